@@ -1,0 +1,194 @@
+/*
+ * bo_b200.h -- C ABI of libbo_b200.so, the B200 (sm_100a) implementation of the
+ * BayesOpt_smart acquisition hot path.
+ *
+ * The reference (alebal123bal/BayesOpt_smart) has no FFI of its own: its hot path is a
+ * set of Python free functions (bayesopt/numba_kernels.py, bayesopt/acquisition.py,
+ * bayesopt/pareto.py) called from bayesopt/bayesian_optimization.py:115-207.  Each entry
+ * point below names the reference function(s) (file:line) it replaces; the Python
+ * package bayesopt_smart_b200 binds them with ctypes behind the
+ * reference's own signatures.
+ *
+ * Conventions
+ *  - plain C: raw pointers, sizes, no torch / C++ types in any signature;
+ *  - every pointer named *_dev is DEVICE memory (FP64 unless stated), every pointer
+ *    named *_host is host memory read synchronously during the call (tiny arrays:
+ *    per-objective hyper-parameters);
+ *  - matrices are row-major with an explicit leading dimension ("ld", in elements);
+ *  - the caller owns all memory; scratch space is passed in as (workspace_dev,
+ *    workspace_bytes) and sized by the matching *_workspace_bytes() query;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all
+ *    work is enqueued on it.  Functions documented as "synchronising" wait for the
+ *    stream before returning because they report a device-side status;
+ *  - return value: 0 = BO_OK, otherwise a BO_ERR_* code; bo_last_error() gives a
+ *    thread-local message.  No exception crosses the boundary;
+ *  - no hidden global state: re-entrant for distinct streams + workspaces.
+ */
+#ifndef BO_B200_H
+#define BO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BO_ABI_VERSION 1
+
+enum {
+  BO_OK = 0,
+  BO_ERR_INVALID = 1,   /* bad argument (null pointer, size out of range, misaligned) */
+  BO_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed               */
+  BO_ERR_NOT_PD = 3,    /* Cholesky met a non-positive pivot (numpy LinAlgError)     */
+  BO_ERR_WORKSPACE = 4  /* workspace_bytes too small                                 */
+};
+
+/* element type of the candidate matrix (`input_space`): the reference builds an int64
+ * Cartesian grid (bayesian_optimization.py:338-340) but its kernels accept floats too */
+enum { BO_CAND_F64 = 0, BO_CAND_I64 = 1 };
+
+#define BO_MAX_OBJECTIVES 4 /* m: number of objectives                          */
+#define BO_MAX_DIMS 16      /* d: input dimensions                               */
+#define BO_MAX_TOPK 1024    /* k of bo_topk_f64                                  */
+#define BO_TILE 128         /* training rows are padded to a multiple of this    */
+
+int bo_abi_version(void);
+const char* bo_last_error(void);
+/* device facts used for grid sizing / roofline reporting */
+int bo_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes, size_t* hbm_bytes);
+
+/* ------------------------------------------------------------------ a1: update_k
+ * RBF Gram matrix K[o,i,j] = var[o] * exp(-0.5*|x_i-x_j|^2 / ls[o]^2) for rows/cols in
+ * [last_eval, current_eval), written symmetric into K_dev (m, ldk, ldk).
+ * Replaces update_k, numba_kernels.py:329-367.                                    */
+int bo_gram_f64(double* K_dev, int ldk, const double* x_dev, int ldx, int last_eval, int current_eval, int d,
+                int m, const double* prior_variance_host, const double* length_scales_host, void* stream);
+
+/* ------------------------------------------------------------------ a2: invert_k
+ * Kinv[o] = (K[o][:n,:n] + jitter*I)^-1, dense (m, n, n) with ld = n.  Computed as
+ * W^T W with W = chol(K + jitter I)^-1 (blocked Cholesky + triangular inverse on DMMA).
+ * Synchronising.  BO_ERR_NOT_PD mirrors numpy.linalg.LinAlgError.
+ * Replaces invert_k, numba_kernels.py:370-403 (jitter = KERNEL_JITTER = 1e-6).     */
+size_t bo_inverse_workspace_bytes(int n, int m);
+int bo_inverse_f64(double* Kinv_dev, const double* K_dev, int ldk, int n, int m, double jitter,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------- a1+a2 fused: the GP factor
+ * Builds everything the scoring pass needs from the training set and keeps it on the
+ * device:  K = gram(x) + jitter I = L L^T,  W = L^-1 (stored tile-packed in the DMMA
+ * fragment order of bo_score_f64),  alpha[o] = K^-1 (y[:,o] - prior_mean[o]).
+ *   wpack_dev : m * bo_wpack_doubles(n) doubles     alpha_dev : m * bo_npad(n) doubles
+ * Synchronising (reports BO_ERR_NOT_PD).
+ * Replaces update_k + invert_k + the "Kinv @ delta_y" half of update_mean
+ * (numba_kernels.py:329-403, :477-483) as called at bayesian_optimization.py:129-142. */
+int bo_npad(int n);
+size_t bo_wpack_doubles(int n);
+size_t bo_fit_workspace_bytes(int n, int m);
+int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int ldx, const double* y_dev, int ldy,
+                  int n, int d, int m, const double* prior_mean_host, const double* prior_variance_host,
+                  const double* length_scales_host, double jitter, void* workspace_dev, size_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------- a3..a8 fused: predict + UCB + sum-UCB
+ * For candidates c in [0, n_cand):  k* (RBF cross kernel, never materialised in API
+ * memory), mu = mu0 + k*.alpha, var = max(var0 - |W k*|^2, min_variance), standardise,
+ * UCB, acq = sum_o ucb[o].  Output arrays are (m, ld_out) / (ld_out,) and any of them
+ * may be NULL (not written).  cand_kind selects f64 / i64 candidates (row-major, ldc).
+ * Asynchronous on `stream`.
+ * Replaces update_k_star, update_mean, update_variance, standardize_objectives
+ * (numba_kernels.py:406-570), update_ucb, update_hypervolume_improvement
+ * (acquisition.py:55-108) as called at bayesian_optimization.py:145-199.           */
+size_t bo_score_workspace_bytes(int n, int m, long long n_cand);
+int bo_score_f64(double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev, double* ucb_dev,
+                 double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
+                 const double* x_dev, int ldx, int n, int d, int m, const double* wpack_dev,
+                 const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
+                 const double* length_scales_host, const double* betas_host, double min_variance,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------- a6..a8 stand-alone (HBM bound)
+ * standardize_objectives + update_ucb + update_hypervolume_improvement on existing
+ * (m, ld) mu / var arrays.  Outputs may be NULL.  numba_kernels.py:538-570,
+ * acquisition.py:55-108.                                                          */
+int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* acq_dev,
+                       const double* mu_dev, const double* var_dev, long long ld, long long n_cand, int m,
+                       const double* prior_mean_host, const double* prior_variance_host, const double* betas_host,
+                       void* stream);
+
+/* ------------------------------------------------------------ a9: select_next_batch
+ * Top-k of acq (value descending, index ascending on ties, NaN last).  Writes k
+ * (value, index + index_base) pairs sorted best-first.  k <= BO_MAX_TOPK.
+ * bo_match_rows_f64 flags, for each listed candidate row, whether it equals (==, all
+ * d coordinates) some evaluated row x[0:n): the exclusion test of acquisition.py:139.
+ * Replaces the argsort + walk of select_next_batch, acquisition.py:116-144.        */
+size_t bo_topk_workspace_bytes(long long n_cand, int k);
+int bo_topk_f64(double* out_val_dev, long long* out_idx_dev, const double* acq_dev, long long n_cand, int k,
+                long long index_base, void* workspace_dev, size_t workspace_bytes, void* stream);
+int bo_match_rows_f64(uint8_t* out_flag_dev, const long long* idx_dev, int n_idx, long long index_base,
+                      const void* cand_dev, int cand_kind, int ldc, const double* x_dev, int ldx, int n, int d,
+                      void* stream);
+/* merge of several sorted-or-not (value, index) lists into the global top-k with the
+ * same comparator (used after the all-gather of per-rank top-k lists).             */
+int bo_topk_merge_f64(double* out_val_dev, long long* out_idx_dev, const double* val_dev, const long long* idx_dev,
+                      int n_pairs, int k, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------- a10: is_pareto_efficient
+ * mask[i] = 1 unless some j has all(y_j >= y_i) and any(y_j > y_i)  (maximisation,
+ * duplicates kept, NaN rows kept).  y is (n, ldy) row-major, m <= BO_MAX_OBJECTIVES.
+ * `against` variant: rows of y are tested against a separate set z (used for the
+ * sample-front prefilter and for the cross-rank union pass).
+ * Replaces is_pareto_efficient, pareto.py:12-45.                                   */
+int bo_pareto_mask_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m, void* stream);
+int bo_pareto_mask_against_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n,
+                               const double* z_dev, long long ldz, long long nz, int m, void* stream);
+
+/* ----------------------------------------------------------------- a11: compute_mll
+ * Batched log marginal likelihood.  For setting s in [0, S): every objective o uses
+ * length scale ls[s*m + o] and jitter jit[s]; the Gram matrix is the pure correlation
+ * matrix (prior_variance cancels, numba_kernels.py:195-197).  out[s] = sum_o mll_o.
+ * Non-PD settings give NaN (no error).  Synchronising.
+ * Replaces compute_mll, numba_kernels.py:152-235 (jit = CHOLESKY_JITTER = 1e-8).    */
+size_t bo_mll_workspace_bytes(int n, int m, int n_settings);
+int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const double* y_dev, int ldy, int n, int d,
+                       int m, const double* prior_mean_host, const double* length_scales_host,
+                       const double* jitter_host, int n_settings, void* workspace_dev, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------ opt-in: exact hypervolume improvement
+ * hvi[i] = HV(front U {u_i}) - HV(front), u_i = (ucb[0][i], .., ucb[m-1][i]), m = 2 or 3.
+ * `front_dev` is (n_front, m) row-major, already non-dominated, clipped to >= ref and
+ * sorted by objective 0 ascending (m=2) / objective 2 descending (m=3).  No reference
+ * counterpart (the reference's "HVI" is sum-UCB, acquisition.py:104-108).           */
+int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n_cand, int m,
+               const double* front_dev, int n_front, const double* ref_host, void* stream);
+
+/* ---------------------------------------------- function-level drop-ins on dense arrays
+ * The reference's free functions exchange a materialised k_star (m, T, M).  These keep
+ * that contract for callers that use the functions one by one.
+ * bo_kstar_dense_f64   : update_k_star, numba_kernels.py:406-442
+ * bo_mean_dense_f64    : update_mean,   numba_kernels.py:450-488
+ * bo_variance_dense_f64: update_variance, numba_kernels.py:491-535                  */
+int bo_kstar_dense_f64(double* kstar_dev, long long ld_row, long long ld_obj, const double* x_dev, int ldx,
+                       const void* cand_dev, int cand_kind, int ldc, long long n_cand, int last_eval,
+                       int current_eval, int d, int m, const double* prior_variance_host,
+                       const double* length_scales_host, void* stream);
+size_t bo_dense_workspace_bytes(int n, long long n_cand);
+int bo_mean_dense_f64(double* mu_dev, long long ld_mu, const double* kstar_dev, long long ld_row, long long ld_obj,
+                      const double* kinv_dev, int ld_kinv, long long ld_kinv_obj, const double* y_dev, int ldy,
+                      const double* prior_mean_host, int n, long long n_cand, int m, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
+int bo_variance_dense_f64(double* var_dev, long long ld_var, const double* kstar_dev, long long ld_row,
+                          long long ld_obj, const double* kinv_dev, int ld_kinv, long long ld_kinv_obj,
+                          const double* prior_variance_host, double min_variance, int n, long long n_cand, int m,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ measurement aid
+ * Plain FP64 GEMM C = A * B^T (row-major, all n x n) on the library's own DMMA kernel;
+ * used by bench.py / tests to report the kernel's throughput next to the roofline.   */
+int bo_dgemm_nt_f64(double* C_dev, const double* A_dev, const double* B_dev, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BO_B200_H */
