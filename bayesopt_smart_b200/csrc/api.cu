@@ -1,0 +1,366 @@
+// api.cu -- the exported C ABI (include/bo_b200.h).  Argument checking, workspace carving, error state.
+#include <stdarg.h>
+
+#include "dense.cuh"
+#include "factor.cuh"
+#include "gemm.cuh"
+#include "mll.cuh"
+#include "score.cuh"
+#include "select.cuh"
+
+namespace bo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return BO_ERR_CUDA;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+static int make_params(ObjParams* hp, int m, const double* mean, const double* var, const double* ls,
+                       const double* beta) {
+  memset(hp, 0, sizeof(*hp));
+  if (m < 1 || m > BO_MAX_OBJECTIVES) {
+    set_error("invalid argument: 1 <= m <= %d required (got %d)", BO_MAX_OBJECTIVES, m);
+    return BO_ERR_INVALID;
+  }
+  for (int o = 0; o < m; ++o) {
+    hp->prior_mean[o] = mean ? mean[o] : 0.0;
+    hp->prior_var[o] = var ? var[o] : 1.0;
+    hp->neg_half_inv_ls2[o] = ls ? -0.5 / (ls[o] * ls[o]) : 0.0;
+    hp->beta[o] = beta ? beta[o] : 0.0;
+  }
+  return BO_OK;
+}
+
+namespace {
+
+// A[o] = K[o][:n,:n] + jitter I, identity padding up to npad
+__global__ void pad_copy_kernel(double* __restrict__ A, int npad, const double* __restrict__ K, int ldk, int n,
+                                double jitter) {
+  const int o = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= npad) return;
+  double v;
+  if (i < n && j < n) {
+    v = K[((long long)o * ldk + i) * ldk + j];
+    if (i == j) v += jitter;
+  } else {
+    v = (i == j) ? 1.0 : 0.0;
+  }
+  A[((long long)o * npad + i) * npad + j] = v;
+}
+
+struct FitBuffers {
+  double *A, *W, *T, *D, *scratch;
+  int* info;
+};
+
+size_t carve_fit(FitBuffers* fb, void* ws, int npad, int m) {
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  size_t off = 0;
+  const size_t mat = align256((size_t)m * npad * npad * sizeof(double));
+  if (fb) fb->A = reinterpret_cast<double*>(p + off);
+  off += mat;
+  if (fb) fb->W = reinterpret_cast<double*>(p + off);
+  off += mat;
+  if (fb) fb->T = reinterpret_cast<double*>(p + off);
+  off += align256((size_t)m * npad * npad / 2 * sizeof(double));
+  if (fb) fb->D = reinterpret_cast<double*>(p + off);
+  off += align256((size_t)m * npad * 64 * sizeof(double));
+  if (fb) fb->scratch = reinterpret_cast<double*>(p + off);
+  off += align256(alpha_scratch_doubles(npad, m) * sizeof(double));
+  if (fb) fb->info = reinterpret_cast<int*>(p + off);
+  off += align256((size_t)m * sizeof(int));
+  return off;
+}
+
+// factor the m padded matrices in fb.A, leave W = L^-1 in fb.W; synchronises to read the pivot status
+int factor_and_invert(const FitBuffers& fb, int npad, int m, cudaStream_t st) {
+  const long long strideA = (long long)npad * npad, strideD = (long long)npad * 64;
+  BO_CUDA(cudaMemsetAsync(fb.info, 0, sizeof(int) * m, st));
+  int rc = cholesky_blocked(fb.A, npad, strideA, npad, m, fb.D, strideD, fb.info, st);
+  if (rc) return rc;
+  rc = tri_inverse(fb.W, npad, strideA, fb.A, npad, strideA, fb.D, strideD, fb.T, strideA / 2, npad, m, st);
+  if (rc) return rc;
+  int info_h[BO_MAX_OBJECTIVES] = {0, 0, 0, 0};
+  BO_CUDA(cudaMemcpyAsync(info_h, fb.info, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  BO_CUDA(cudaStreamSynchronize(st));
+  for (int o = 0; o < m; ++o) {
+    if (info_h[o] != 0) {
+      set_error("Matrix is not positive definite (objective %d, pivot %d)", o, info_h[o]);
+      return BO_ERR_NOT_PD;
+    }
+  }
+  return BO_OK;
+}
+
+}  // namespace
+}  // namespace bo
+
+using namespace bo;
+
+extern "C" {
+
+int bo_abi_version(void) { return BO_ABI_VERSION; }
+const char* bo_last_error(void) { return g_err; }
+
+int bo_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes, size_t* hbm_bytes) {
+  int dev = 0;
+  BO_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  BO_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
+  if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+  return BO_OK;
+}
+
+int bo_npad(int n) { return round_up(n, TM); }
+size_t bo_wpack_doubles(int n) { return (size_t)wpack_tile_offset(round_up(n, TM) / TM) * TILE_DOUBLES; }
+
+int bo_gram_f64(double* K_dev, int ldk, const double* x_dev, int ldx, int last_eval, int current_eval, int d, int m,
+                const double* prior_variance_host, const double* length_scales_host, void* stream) {
+  BO_REQUIRE(K_dev && x_dev && prior_variance_host && length_scales_host, "null pointer");
+  BO_REQUIRE(d >= 1 && d <= BO_MAX_DIMS, "1 <= d <= 16");
+  BO_REQUIRE(last_eval >= 0 && current_eval >= last_eval && current_eval <= ldk, "bad evaluation range");
+  ObjParams hp;
+  int rc = make_params(&hp, m, nullptr, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  return gram(K_dev, ldk, (long long)ldk * ldk, x_dev, ldx, last_eval, current_eval, current_eval, d, m, hp, 0.0,
+              (cudaStream_t)stream);
+}
+
+size_t bo_inverse_workspace_bytes(int n, int m) { return carve_fit(nullptr, nullptr, round_up(n, TM), m); }
+
+int bo_inverse_f64(double* Kinv_dev, const double* K_dev, int ldk, int n, int m, double jitter, void* workspace_dev,
+                   size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(Kinv_dev && K_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(n >= 1 && n <= ldk && m >= 1 && m <= BO_MAX_OBJECTIVES, "bad sizes");
+  const int npad = round_up(n, TM);
+  if (workspace_bytes < bo_inverse_workspace_bytes(n, m)) {
+    set_error("inverse workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FitBuffers fb;
+  carve_fit(&fb, workspace_dev, npad, m);
+  pad_copy_kernel<<<dim3((npad + 127) / 128, npad, m), 128, 0, st>>>(fb.A, npad, K_dev, ldk, n, jitter);
+  BO_LAUNCH_CHECK("pad_copy_kernel");
+  int rc = factor_and_invert(fb, npad, m, st);
+  if (rc) return rc;
+  GemmArgs g;  // Kinv = W^T W   (C[i][j] = sum_k W[k][i] W[k][j])
+  g.M = n; g.N = n; g.K = npad;
+  g.A = fb.W; g.lda = npad; g.strideA = (long long)npad * npad;
+  g.B = fb.W; g.ldb = npad; g.strideB = (long long)npad * npad;
+  g.C = Kinv_dev; g.ldc = n; g.strideC = (long long)n * n;
+  g.batch = m;
+  rc = gemm(g, 1, 1, st);
+  if (rc) return rc;
+  BO_CUDA(cudaStreamSynchronize(st));
+  return BO_OK;
+}
+
+size_t bo_fit_workspace_bytes(int n, int m) { return carve_fit(nullptr, nullptr, round_up(n, TM), m); }
+
+int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int ldx, const double* y_dev, int ldy,
+                  int n, int d, int m, const double* prior_mean_host, const double* prior_variance_host,
+                  const double* length_scales_host, double jitter, void* workspace_dev, size_t workspace_bytes,
+                  void* stream) {
+  BO_REQUIRE(wpack_dev && alpha_dev && x_dev && y_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host, "null hyper-parameter pointer");
+  BO_REQUIRE(n >= 1 && d >= 1 && d <= BO_MAX_DIMS, "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  const int npad = round_up(n, TM);
+  if (workspace_bytes < bo_fit_workspace_bytes(n, m)) {
+    set_error("fit workspace too small: %zu < %zu", workspace_bytes, bo_fit_workspace_bytes(n, m));
+    return BO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FitBuffers fb;
+  carve_fit(&fb, workspace_dev, npad, m);
+  const long long strideA = (long long)npad * npad;
+  rc = gram(fb.A, npad, strideA, x_dev, ldx, 0, n, npad, d, m, hp, jitter, st);
+  if (rc) return rc;
+  rc = factor_and_invert(fb, npad, m, st);
+  if (rc) return rc;
+  rc = compute_alpha(alpha_dev, fb.W, npad, strideA, y_dev, ldy, n, npad, m, hp, fb.scratch, st);
+  if (rc) return rc;
+  rc = pack_w(wpack_dev, (long long)bo_wpack_doubles(n), fb.W, npad, strideA, npad, m, st);
+  if (rc) return rc;
+  BO_CUDA(cudaStreamSynchronize(st));
+  return BO_OK;
+}
+
+size_t bo_score_workspace_bytes(int n, int m, long long n_cand) {
+  return score_workspace_bytes(make_score_plan(n, m, n_cand));
+}
+
+int bo_score_f64(double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev, double* ucb_dev,
+                 double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
+                 const double* x_dev, int ldx, int n, int d, int m, const double* wpack_dev, const double* alpha_dev,
+                 const double* prior_mean_host, const double* prior_variance_host, const double* length_scales_host,
+                 const double* betas_host, double min_variance, void* workspace_dev, size_t workspace_bytes,
+                 void* stream) {
+  BO_REQUIRE(cand_dev && x_dev && wpack_dev && alpha_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host && betas_host,
+             "null hyper-parameter pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(n >= 1 && d >= 1 && d <= BO_MAX_DIMS && ldc >= d && ld_out >= n_cand, "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, betas_host);
+  if (rc) return rc;
+  ScoreOutputs out;
+  out.mu = mu_dev; out.var = var_dev; out.std_mu = std_mu_dev; out.std_var = std_var_dev;
+  out.ucb = ucb_dev; out.acq = acq_dev; out.ld = ld_out;
+  return score_candidates(out, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, m, wpack_dev, alpha_dev, hp,
+                          min_variance, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* acq_dev,
+                       const double* mu_dev, const double* var_dev, long long ld, long long n_cand, int m,
+                       const double* prior_mean_host, const double* prior_variance_host, const double* betas_host,
+                       void* stream) {
+  BO_REQUIRE(mu_dev && var_dev && prior_mean_host && prior_variance_host && betas_host, "null pointer");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, nullptr, betas_host);
+  if (rc) return rc;
+  return acquisition_only(std_mu_dev, std_var_dev, ucb_dev, acq_dev, mu_dev, var_dev, ld, n_cand, m, hp,
+                          (cudaStream_t)stream);
+}
+
+size_t bo_topk_workspace_bytes(long long n_cand, int k) { return topk_workspace_bytes(n_cand, k); }
+
+int bo_topk_f64(double* out_val_dev, long long* out_idx_dev, const double* acq_dev, long long n_cand, int k,
+                long long index_base, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(out_val_dev && out_idx_dev && acq_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(k >= 1 && k <= BO_MAX_TOPK && n_cand >= 1, "1 <= k <= 1024, n_cand >= 1");
+  return topk_levels(out_val_dev, out_idx_dev, acq_dev, nullptr, n_cand, k, index_base, workspace_dev,
+                     workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_topk_merge_f64(double* out_val_dev, long long* out_idx_dev, const double* val_dev, const long long* idx_dev,
+                      int n_pairs, int k, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(out_val_dev && out_idx_dev && val_dev && idx_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(k >= 1 && k <= BO_MAX_TOPK && n_pairs >= 1, "1 <= k <= 1024, n_pairs >= 1");
+  return topk_levels(out_val_dev, out_idx_dev, val_dev, idx_dev, n_pairs, k, 0, workspace_dev, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+int bo_match_rows_f64(uint8_t* out_flag_dev, const long long* idx_dev, int n_idx, long long index_base,
+                      const void* cand_dev, int cand_kind, int ldc, const double* x_dev, int ldx, int n, int d,
+                      void* stream) {
+  BO_REQUIRE(out_flag_dev && idx_dev && cand_dev && (x_dev || n == 0), "null pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  return match_rows(out_flag_dev, idx_dev, n_idx, index_base, cand_dev, cand_kind, ldc, x_dev, ldx, n, d,
+                    (cudaStream_t)stream);
+}
+
+int bo_pareto_mask_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m, void* stream) {
+  BO_REQUIRE(mask_dev && y_dev, "null pointer");
+  BO_REQUIRE(m >= 1 && m <= BO_MAX_OBJECTIVES && ldy >= m, "bad sizes");
+  return pareto_mask(mask_dev, y_dev, ldy, n, y_dev, ldy, n, m, (cudaStream_t)stream);
+}
+
+int bo_pareto_mask_against_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n,
+                               const double* z_dev, long long ldz, long long nz, int m, void* stream) {
+  BO_REQUIRE(mask_dev && y_dev && (z_dev || nz == 0), "null pointer");
+  BO_REQUIRE(m >= 1 && m <= BO_MAX_OBJECTIVES && ldy >= m && ldz >= m, "bad sizes");
+  return pareto_mask(mask_dev, y_dev, ldy, n, z_dev, ldz, nz, m, (cudaStream_t)stream);
+}
+
+size_t bo_mll_workspace_bytes(int n, int m, int n_settings) { return mll_workspace_bytes(n, m, n_settings); }
+
+int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const double* y_dev, int ldy, int n, int d,
+                       int m, const double* prior_mean_host, const double* length_scales_host,
+                       const double* jitter_host, int n_settings, void* workspace_dev, size_t workspace_bytes,
+                       void* stream) {
+  BO_REQUIRE(out_dev && x_dev && y_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && length_scales_host && jitter_host, "null hyper-parameter pointer");
+  BO_REQUIRE(n >= 1 && n <= 16384 && d >= 1 && d <= BO_MAX_DIMS && m >= 1 && m <= BO_MAX_OBJECTIVES &&
+                 n_settings >= 1,
+             "bad sizes");
+  return mll_batched(out_dev, x_dev, ldx, y_dev, ldy, n, d, m, prior_mean_host, length_scales_host, jitter_host,
+                     n_settings, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n_cand, int m,
+               const double* front_dev, int n_front, const double* ref_host, void* stream) {
+  BO_REQUIRE(hvi_dev && ucb_dev && ref_host && (front_dev || n_front == 0), "null pointer");
+  BO_REQUIRE(m == 2 || m == 3, "exact HVI supports 2 or 3 objectives");
+  return hvi(hvi_dev, ucb_dev, ld, n_cand, m, front_dev, n_front, ref_host, (cudaStream_t)stream);
+}
+
+int bo_kstar_dense_f64(double* kstar_dev, long long ld_row, long long ld_obj, const double* x_dev, int ldx,
+                       const void* cand_dev, int cand_kind, int ldc, long long n_cand, int last_eval,
+                       int current_eval, int d, int m, const double* prior_variance_host,
+                       const double* length_scales_host, void* stream) {
+  BO_REQUIRE(kstar_dev && x_dev && cand_dev && prior_variance_host && length_scales_host, "null pointer");
+  BO_REQUIRE(d >= 1 && d <= BO_MAX_DIMS, "1 <= d <= 16");
+  ObjParams hp;
+  int rc = make_params(&hp, m, nullptr, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  return kstar_dense(kstar_dev, ld_row, ld_obj, x_dev, ldx, cand_dev, cand_kind, ldc, n_cand, last_eval, current_eval,
+                     d, m, hp, (cudaStream_t)stream);
+}
+
+size_t bo_dense_workspace_bytes(int n, long long n_cand) { return dense_workspace_bytes(n, n_cand); }
+
+int bo_mean_dense_f64(double* mu_dev, long long ld_mu, const double* kstar_dev, long long ld_row, long long ld_obj,
+                      const double* kinv_dev, int ld_kinv, long long ld_kinv_obj, const double* y_dev, int ldy,
+                      const double* prior_mean_host, int n, long long n_cand, int m, void* workspace_dev,
+                      size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(mu_dev && kstar_dev && kinv_dev && y_dev && prior_mean_host && workspace_dev, "null pointer");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  return mean_dense(mu_dev, ld_mu, kstar_dev, ld_row, ld_obj, kinv_dev, ld_kinv, ld_kinv_obj, y_dev, ldy, hp, n,
+                    n_cand, m, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_variance_dense_f64(double* var_dev, long long ld_var, const double* kstar_dev, long long ld_row,
+                          long long ld_obj, const double* kinv_dev, int ld_kinv, long long ld_kinv_obj,
+                          const double* prior_variance_host, double min_variance, int n, long long n_cand, int m,
+                          void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(var_dev && kstar_dev && kinv_dev && prior_variance_host && workspace_dev, "null pointer");
+  ObjParams hp;
+  int rc = make_params(&hp, m, nullptr, prior_variance_host, nullptr, nullptr);
+  if (rc) return rc;
+  return variance_dense(var_dev, ld_var, kstar_dev, ld_row, ld_obj, kinv_dev, ld_kinv, ld_kinv_obj, hp, min_variance,
+                        n, n_cand, m, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_dgemm_nt_f64(double* C_dev, const double* A_dev, const double* B_dev, int n, void* stream) {
+  BO_REQUIRE(C_dev && A_dev && B_dev && n >= 1, "bad arguments");
+  GemmArgs g;
+  g.M = g.N = g.K = n;
+  g.A = A_dev; g.lda = n;
+  g.B = B_dev; g.ldb = n;
+  g.C = C_dev; g.ldc = n;
+  return gemm(g, 0, 0, (cudaStream_t)stream);
+}
+
+}  // extern "C"

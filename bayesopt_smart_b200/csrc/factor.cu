@@ -1,0 +1,314 @@
+// factor.cu -- training-side factorisation, once per BO iteration (reference: update_k + invert_k,
+// numba_kernels.py:329-403).  All matrices here are npad x npad (npad = n rounded up to 128) with an
+// identity block in the padding, so every GEMM below runs on whole tiles.
+//
+//   gram_kernel        K = var * exp(-0.5 |xi-xj|^2 / ls^2) (+ diag_add), identity padding
+//   potf2_inv_kernel   64x64 diagonal block: in-shared-memory Cholesky and its triangular inverse
+//   cholesky_blocked   right-looking: potf2 -> panel (GEMM with the inverted block) -> trailing SYRK (DMMA)
+//   tri_inverse        W = L^-1 by recursive doubling: W21 = -W22 (L21 W11), two batched GEMMs per level
+//   alpha kernels      alpha = W^T (W (y - mu0))
+//   pack_w_kernel      W -> 16 KB tiles in DMMA fragment order for trmm.cu
+#include "factor.cuh"
+#include "gemm.cuh"
+
+namespace bo {
+
+namespace {
+
+constexpr int NB = 64;
+
+// ----------------------------------------------------------------------------------------- gram
+__global__ void gram_kernel(double* __restrict__ K, long long ldk, long long strideK, const double* __restrict__ x,
+                            int ldx, int last_eval, int n, int npad_rows, int d, int m, ObjParams hp,
+                            double diag_add) {
+  // 16x16 pairs per block over the index range [last_eval, npad_rows); only tiles with bj >= bi
+  if (blockIdx.x < blockIdx.y) return;
+  const int i = last_eval + blockIdx.y * 16 + threadIdx.y;
+  const int j = last_eval + blockIdx.x * 16 + threadIdx.x;
+  if (i >= npad_rows || j >= npad_rows || j < i) return;
+  if (i >= n || j >= n) {
+    // identity padding keeps the padded factor trivially L = W = I
+    const double v = (i == j) ? 1.0 : 0.0;
+    for (int o = 0; o < m; ++o) {
+      K[o * strideK + (long long)i * ldk + j] = v;
+      K[o * strideK + (long long)j * ldk + i] = v;
+    }
+    return;
+  }
+  double sq = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double diff = x[(long long)i * ldx + k] - x[(long long)j * ldx + k];
+    sq = fma(diff, diff, sq);
+  }
+  for (int o = 0; o < m; ++o) {
+    double v = hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]);
+    if (i == j) v += diag_add;
+    K[o * strideK + (long long)i * ldk + j] = v;
+    K[o * strideK + (long long)j * ldk + i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------- potf2 + inverse
+// One CTA per matrix in the batch.  S = lower Cholesky factor of the 64x64 diagonal block, X = S^-1.
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                        double* __restrict__ D, long long strideD,
+                                                        int* __restrict__ info, int j0) {
+  extern __shared__ double sm[];
+  double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
+  double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  double* Ab = A + (long long)blockIdx.x * strideA + (long long)j0 * lda + j0;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    S[r][c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
+    X[r][c] = 0.0;
+  }
+  __syncthreads();
+  const int ur = tid >> 2, uc0 = tid & 3;  // trailing update: row ur, columns uc0 + 4q
+  for (int j = 0; j < NB; ++j) {
+    __syncthreads();  // trailing update of the previous column is complete
+    const double piv = S[j][j];
+    if (tid == 0 && !(piv > 0.0)) bad = (bad == 0) ? (j0 + j + 1) : bad;
+    const double dsq = sqrt(piv);
+    __syncthreads();
+    if (tid < NB) {
+      if (tid == j) S[j][j] = dsq;
+      else if (tid > j) S[tid][j] = S[tid][j] / dsq;
+    }
+    __syncthreads();
+    if (ur > j) {
+      const double lij = S[ur][j];
+#pragma unroll 4
+      for (int q = 0; q < 16; ++q) {
+        const int k = uc0 + 4 * q;
+        if (k > j && k <= ur) S[ur][k] = fma(-lij, S[k][j], S[ur][k]);
+      }
+    }
+  }
+  __syncthreads();
+  // X = S^-1 by forward substitution; 4 threads per column split the dot product over k mod 4.
+  // The i loop is uniform across the warp (columns differ per lane) so the shuffles are convergent.
+  {
+    const int c = tid >> 2, q = tid & 3;
+    if (q == 0) X[c][c] = 1.0 / S[c][c];
+    __syncwarp();
+    for (int i = 1; i < NB; ++i) {
+      double s = 0.0;
+      if (i > c)
+        for (int k = c + q; k < i; k += 4) s = fma(S[i][k], X[k][c], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0 && i > c) X[i][c] = -s / S[i][i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  double* Db = D + (long long)blockIdx.x * strideD;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Ab[(long long)r * lda + c] = S[r][c];  // strict upper part of the block becomes exact zeros
+    Db[e] = X[r][c];
+  }
+  if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, bad);
+}
+
+// ----------------------------------------------------------------------------------------- small helpers
+__global__ void copy_diag_blocks_kernel(double* __restrict__ W, long long ldw, long long strideW,
+                                        const double* __restrict__ D, long long strideD) {
+  // grid (nblk, batch): W[jb*64.., jb*64..] = D[jb]
+  const int jb = blockIdx.x;
+  const double* Db = D + (long long)blockIdx.y * strideD + (long long)jb * NB * NB;
+  double* Wb = W + (long long)blockIdx.y * strideW + (long long)jb * NB * (ldw + 1);
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Wb[(long long)(e >> 6) * ldw + (e & 63)] = Db[e];
+}
+
+// u[i] = sum_{k<=i} W[i][k] * (y[k*ldy + o] - mu0)     (one warp per row)
+__global__ void gemv_lower_delta_kernel(double* __restrict__ u, const double* __restrict__ W, long long ldw,
+                                        long long strideW, const double* __restrict__ y, int ldy, int n, int npad,
+                                        ObjParams hp) {
+  const int o = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double* Wr = W + o * strideW + (long long)row * ldw;
+  double s = 0.0;
+  const int kend = min(row + 1, n);
+  for (int k = lane; k < kend; k += 32) s = fma(Wr[k], y[(long long)k * ldy + o] - hp.prior_mean[o], s);
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) u[(long long)o * npad + row] = s;
+}
+
+// part[rs][j] = sum over rows i in split rs of W[i][j] * u[i]   (thread per column, coalesced)
+__global__ void gemvT_lower_partial_kernel(double* __restrict__ part, const double* __restrict__ W, long long ldw,
+                                           long long strideW, const double* __restrict__ u, int npad, int rows_per) {
+  const int o = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  const int i0 = max(blockIdx.y * rows_per, j), i1 = min((blockIdx.y + 1) * rows_per, npad);
+  const double* Wo = W + o * strideW;
+  const double* uo = u + (long long)o * npad;
+  double s = 0.0;
+  for (int i = i0; i < i1; ++i) s = fma(Wo[(long long)i * ldw + j], uo[i], s);
+  part[((long long)o * gridDim.y + blockIdx.y) * npad + j] = s;
+}
+__global__ void sum_partials_kernel(double* __restrict__ out, const double* __restrict__ part, int npad, int nsplit) {
+  const int o = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  double s = 0.0;
+  for (int r = 0; r < nsplit; ++r) s += part[((long long)o * nsplit + r) * npad + j];
+  out[(long long)o * npad + j] = s;
+}
+
+// ----------------------------------------------------------------------------------------- pack W
+// tile (ib, kt) of W (128 rows x 16 k) -> [wm(2)][i(8)][sp(2)][lane(32)][q(2)]
+//   element = W[ib*128 + wm*64 + i*8 + g][kt*16 + (sp*2+q)*4 + t],  lane = g*4 + t
+__global__ void __launch_bounds__(256) pack_w_kernel(double* __restrict__ Wp, long long strideWp,
+                                                     const double* __restrict__ W, long long ldw, long long strideW,
+                                                     int nb) {
+  __shared__ double s[TM][TK + 1];
+  const int o = blockIdx.y;
+  // decode tile index -> (ib, kt)
+  long long tile = blockIdx.x;
+  int ib = 0;
+  while (wpack_tile_offset(ib + 1) <= tile) ++ib;
+  const int kt = (int)(tile - wpack_tile_offset(ib));
+  const double* src = W + o * strideW + (long long)ib * TM * ldw + (long long)kt * TK;
+  for (int e = threadIdx.x; e < TM * TK / 2; e += 256) {
+    const int r = e >> 3, c2 = (e & 7) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(src + (long long)r * ldw + c2);
+    s[r][c2] = v.x;
+    s[r][c2 + 1] = v.y;
+  }
+  __syncthreads();
+  double* dst = Wp + o * strideWp + tile * TILE_DOUBLES;
+  for (int e = threadIdx.x; e < TILE_DOUBLES; e += 256) {
+    const int q = e & 1, lane = (e >> 1) & 31, sp = (e >> 6) & 1, i = (e >> 7) & 7, wm = e >> 10;
+    const int g = lane >> 2, t = lane & 3;
+    dst[e] = s[wm * 64 + i * 8 + g][(sp * 2 + q) * 4 + t];
+  }
+  (void)nb;
+}
+
+}  // namespace
+
+// =========================================================================================== host drivers
+int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, int last_eval, int n, int npad_rows,
+         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream) {
+  const int span = npad_rows - last_eval;
+  if (span <= 0) return BO_OK;
+  const int nt = (span + 15) / 16;
+  gram_kernel<<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d, m, hp,
+                                                         diag_add);
+  BO_LAUNCH_CHECK("gram_kernel");
+  return BO_OK;
+}
+
+int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int batch, double* D, long long strideD,
+                     int* info, cudaStream_t stream) {
+  static bool attr_set = false;
+  const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
+  if (!attr_set) {
+    BO_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  for (int j0 = 0; j0 < npad; j0 += NB) {
+    double* Dj = D + (long long)(j0 / NB) * NB * NB;
+    potf2_inv_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, Dj, strideD, info, j0);
+    BO_LAUNCH_CHECK("potf2_inv_kernel");
+    const int r = npad - j0 - NB;
+    if (r <= 0) break;
+    double* P = A + (long long)(j0 + NB) * lda + j0;
+    GemmArgs p;  // P <- P * Linv^T   (C[i][c] = sum_k P[i][k] Linv[c][k]); one column tile => in place is safe
+    p.M = r; p.N = NB; p.K = NB;
+    p.A = P; p.lda = lda; p.strideA = strideA;
+    p.B = Dj; p.ldb = NB; p.strideB = strideD;
+    p.C = P; p.ldc = lda; p.strideC = strideA;
+    p.batch = batch;
+    int rc = gemm(p, 0, 0, stream);
+    if (rc) return rc;
+    GemmArgs t;  // trailing -= P P^T (lower tiles only)
+    t.M = r; t.N = r; t.K = NB; t.alpha = -1.0; t.beta = 1.0;
+    t.A = P; t.lda = lda; t.strideA = strideA;
+    t.B = P; t.ldb = lda; t.strideB = strideA;
+    t.C = A + (long long)(j0 + NB) * (lda + 1); t.ldc = lda; t.strideC = strideA;
+    t.batch = batch; t.lower_only = 1;
+    rc = gemm(t, 0, 0, stream);
+    if (rc) return rc;
+  }
+  return BO_OK;
+}
+
+int tri_inverse(double* W, long long ldw, long long strideW, const double* L, long long ldl, long long strideL,
+                const double* D, long long strideD, double* T, long long strideT, int npad, int batch,
+                cudaStream_t stream) {
+  BO_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)strideW * batch, stream));
+  copy_diag_blocks_kernel<<<dim3(npad / NB, batch), 256, 0, stream>>>(W, ldw, strideW, D, strideD);
+  BO_LAUNCH_CHECK("copy_diag_blocks_kernel");
+  for (int s = NB; s < npad; s *= 2) {
+    const int full_pairs = npad / (2 * s);
+    const int rem = npad % (2 * s);
+    const int r2_tail = rem > s ? rem - s : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: all full pairs, batched per matrix; pass 1: the ragged last pair
+      const int npairs = pass == 0 ? full_pairs : (r2_tail > 0 ? 1 : 0);
+      if (npairs == 0) continue;
+      const int r2 = pass == 0 ? s : r2_tail;
+      const long long o0 = pass == 0 ? 0 : (long long)full_pairs * 2 * s;
+      for (int b = 0; b < batch; ++b) {
+        const double* Lb = L + b * strideL;
+        double* Wb = W + b * strideW;
+        double* Tb = T + b * strideT;
+        GemmArgs a;  // T = L21 * W11
+        a.M = r2; a.N = s; a.K = s;
+        a.A = Lb + (o0 + s) * ldl + o0; a.lda = ldl; a.strideA = 2LL * s * (ldl + 1);
+        a.B = Wb + o0 * (ldw + 1); a.ldb = ldw; a.strideB = 2LL * s * (ldw + 1);
+        a.C = Tb; a.ldc = s; a.strideC = (long long)s * s;
+        a.batch = npairs; a.k_start_cols = 1;
+        int rc = gemm(a, 0, 1, stream);
+        if (rc) return rc;
+        GemmArgs c;  // W21 = -W22 * T
+        c.M = r2; c.N = s; c.K = r2; c.alpha = -1.0;
+        c.A = Wb + (o0 + s) * (ldw + 1); c.lda = ldw; c.strideA = 2LL * s * (ldw + 1);
+        c.B = Tb; c.ldb = s; c.strideB = (long long)s * s;
+        c.C = Wb + (o0 + s) * ldw + o0; c.ldc = ldw; c.strideC = 2LL * s * (ldw + 1);
+        c.batch = npairs; c.k_limit_rows = 1;
+        rc = gemm(c, 0, 1, stream);
+        if (rc) return rc;
+      }
+    }
+  }
+  return BO_OK;
+}
+
+int compute_alpha(double* alpha, const double* W, long long ldw, long long strideW, const double* y, int ldy, int n,
+                  int npad, int m, const ObjParams& hp, double* scratch, cudaStream_t stream) {
+  // scratch: m*npad (u) + m*NSPLIT*npad (partials)
+  const int NSPLIT = 16;
+  double* u = scratch;
+  double* part = scratch + (size_t)m * npad;
+  gemv_lower_delta_kernel<<<dim3((npad + 7) / 8, m), 256, 0, stream>>>(u, W, ldw, strideW, y, ldy, n, npad, hp);
+  BO_LAUNCH_CHECK("gemv_lower_delta_kernel");
+  const int rows_per = (npad + NSPLIT - 1) / NSPLIT;
+  gemvT_lower_partial_kernel<<<dim3((npad + 127) / 128, NSPLIT, m), 128, 0, stream>>>(part, W, ldw, strideW, u, npad,
+                                                                                     rows_per);
+  BO_LAUNCH_CHECK("gemvT_lower_partial_kernel");
+  sum_partials_kernel<<<dim3((npad + 127) / 128, m), 128, 0, stream>>>(alpha, part, npad, NSPLIT);
+  BO_LAUNCH_CHECK("sum_partials_kernel");
+  return BO_OK;
+}
+size_t alpha_scratch_doubles(int npad, int m) { return (size_t)m * npad * 17; }
+
+int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int m,
+           cudaStream_t stream) {
+  const int nb = npad / TM;
+  const long long ntiles = wpack_tile_offset(nb);
+  pack_w_kernel<<<dim3((unsigned)ntiles, m), 256, 0, stream>>>(Wp, strideWp, W, ldw, strideW, nb);
+  BO_LAUNCH_CHECK("pack_w_kernel");
+  return BO_OK;
+}
+
+}  // namespace bo

@@ -1,0 +1,30 @@
+// factor.cuh -- host drivers of the training-side factorisation (factor.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bo {
+
+// K (m, ldk, ldk): RBF Gram over rows/cols [last_eval, npad_rows); indices >= n get identity padding.
+int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, int last_eval, int n, int npad_rows,
+         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream);
+
+// In-place lower Cholesky of `batch` npad x npad matrices (npad % 64 == 0).  D receives the inverted 64x64
+// diagonal blocks (npad/64 blocks of 4096 doubles per matrix).  info[b] = 1-based failing pivot or 0.
+int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int batch, double* D, long long strideD,
+                     int* info, cudaStream_t stream);
+
+// W = L^-1 (lower), T is scratch of npad*npad/2 doubles per matrix.
+int tri_inverse(double* W, long long ldw, long long strideW, const double* L, long long ldl, long long strideL,
+                const double* D, long long strideD, double* T, long long strideT, int npad, int batch,
+                cudaStream_t stream);
+
+// alpha[o] = W_o^T (W_o (y[:,o] - mu0_o)), (m, npad)
+int compute_alpha(double* alpha, const double* W, long long ldw, long long strideW, const double* y, int ldy, int n,
+                  int npad, int m, const ObjParams& hp, double* scratch, cudaStream_t stream);
+size_t alpha_scratch_doubles(int npad, int m);
+
+// W -> fragment-ordered 16 KB tiles (see common.cuh)
+int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int m,
+           cudaStream_t stream);
+
+}  // namespace bo

@@ -1,0 +1,193 @@
+// mll.cu -- batched log marginal likelihood over many (length-scale, jitter) settings.
+// Reference: compute_mll, numba_kernels.py:152-235.  Per setting s and objective o:
+//   R = exp(-0.5 |xi-xj|^2 / ls^2) + jit I          (the reference divides K by prior_variance: :195-197)
+//   yt = (y - mu0) / std(y - mu0)                    (:201-208, population std, skipped when 0)
+//   L = chol(R)                                      (:211-214)      -> cholesky_blocked (DMMA)
+//   mll = -0.5 |L^-1 yt|^2 - sum(log diag L) - 0.5 n log(2 pi)     (:216-232; yt.alpha == |L^-1 yt|^2)
+#include "factor.cuh"
+#include "mll.cuh"
+
+namespace bo {
+
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  // deterministic tree: warp shuffles then the first warp over the 8 partials
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
+  return s;
+}
+
+// one CTA per objective: standardised targets, zero padded to npad
+__global__ void __launch_bounds__(256) mll_prepare_y_kernel(double* __restrict__ yt, const double* __restrict__ y,
+                                                            int ldy, int n, int npad, ObjParams hp) {
+  __shared__ double scratch[8];
+  const int o = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += y[(long long)i * ldy + o] - hp.prior_mean[o];
+  const double mean = block_sum(s, scratch) / n;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double c = (y[(long long)i * ldy + o] - hp.prior_mean[o]) - mean;
+    v = fma(c, c, v);
+  }
+  const double sd = sqrt(block_sum(v, scratch) / n);
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    double c = 0.0;
+    if (i < n) {
+      c = y[(long long)i * ldy + o] - hp.prior_mean[o];
+      if (sd > 0.0) c /= sd;
+    }
+    yt[(long long)o * npad + i] = c;
+  }
+}
+
+// one CTA per matrix: forward substitution z = L^-1 yt using the inverted 64x64 diagonal blocks,
+// then the three MLL terms.  z lives in shared memory.
+__global__ void __launch_bounds__(256)
+    mll_solve_kernel(double* __restrict__ mll_obj, const double* __restrict__ L, long long ldl, long long strideL,
+                     const double* __restrict__ D, long long strideD, const int* __restrict__ info,
+                     const double* __restrict__ yt, int n, int npad, int m) {
+  extern __shared__ double zsm[];  // npad (z) + 64 (rhs) + 8 (scratch)
+  double* z = zsm;
+  double* rhs = zsm + npad;
+  double* scratch = rhs + 64;
+  const int b = blockIdx.x;
+  const int o = b % m;
+  const double* Lb = L + (long long)b * strideL;
+  const double* Db = D + (long long)b * strideD;
+  const double* yo = yt + (long long)o * npad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = npad / 64;
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int r0 = jb * 64;
+    // rhs[r] = yt[r0+r] - sum_{k<r0} L[r0+r][k] z[k]; warp w owns rows 8w..8w+7
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = warp * 8 + rr;
+      const double* Lr = Lb + (long long)(r0 + r) * ldl;
+      double s = 0.0;
+      for (int k = lane; k < r0; k += 32) s = fma(Lr[k], z[k], s);
+#pragma unroll
+      for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) rhs[r] = yo[r0 + r] - s;
+    }
+    __syncthreads();
+    // z[r0 + r] = sum_{c<=r} Dinv[r][c] rhs[c]; 4 threads per row
+    {
+      const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+      const double* Dr = Db + (long long)jb * 4096 + r * 64;
+      double s = 0.0;
+      for (int c = q; c <= r; c += 4) s = fma(Dr[c], rhs[c], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) z[r0 + r] = s;
+    }
+    __syncthreads();
+  }
+  double fit = 0.0, logdiag = 0.0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    fit = fma(z[i], z[i], fit);
+    logdiag += log(Lb[(long long)i * (ldl + 1)]);
+  }
+  fit = block_sum(fit, scratch);
+  logdiag = block_sum(logdiag, scratch);
+  if (threadIdx.x == 0) {
+    double v = -0.5 * fit - logdiag - 0.5 * n * log(2.0 * 3.14159265358979323846);
+    if (info[b] != 0) v = __longlong_as_double(0x7ff8000000000000ll);
+    mll_obj[b] = v;
+  }
+}
+
+__global__ void mll_sum_kernel(double* __restrict__ out, const double* __restrict__ mll_obj, int n_settings, int m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_settings) return;
+  double t = 0.0;
+  for (int o = 0; o < m; ++o) t += mll_obj[(long long)s * m + o];  // np.sum over objectives (:235)
+  out[s] = t;
+}
+
+}  // namespace
+
+static int group_settings(int npad, int m, int n_settings) {
+  // settings factored together: keep the matrices of one group near 4 GB
+  const size_t per = (size_t)m * npad * npad * sizeof(double);
+  size_t g = ((size_t)4 << 30) / per;
+  if (g < 1) g = 1;
+  if (g > (size_t)n_settings) g = n_settings;
+  return (int)g;
+}
+
+size_t mll_workspace_bytes(int n, int m, int n_settings) {
+  const int npad = round_up(n, TM);
+  const int gs = group_settings(npad, m, n_settings);
+  size_t b = 0;
+  b += align256((size_t)gs * m * npad * npad * sizeof(double));   // matrices
+  b += align256((size_t)gs * m * npad * 64 * sizeof(double));     // inverted diagonal blocks
+  b += align256((size_t)gs * m * sizeof(int));                    // info
+  b += align256((size_t)m * npad * sizeof(double));               // standardised targets
+  b += align256((size_t)n_settings * m * sizeof(double));         // per-objective values
+  return b;
+}
+
+int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy, int n, int d, int m,
+                const double* prior_mean, const double* length_scales, const double* jitter, int n_settings,
+                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < mll_workspace_bytes(n, m, n_settings)) {
+    set_error("mll workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  const int npad = round_up(n, TM);
+  const int gs = group_settings(npad, m, n_settings);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  size_t off = 0;
+  double* A = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * npad * sizeof(double));
+  double* D = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * 64 * sizeof(double));
+  int* info = reinterpret_cast<int*>(ws + off);       off += align256((size_t)gs * m * sizeof(int));
+  double* yt = reinterpret_cast<double*>(ws + off);   off += align256((size_t)m * npad * sizeof(double));
+  double* vals = reinterpret_cast<double*>(ws + off);
+
+  ObjParams hp0;
+  memset(&hp0, 0, sizeof(hp0));
+  for (int o = 0; o < m; ++o) hp0.prior_mean[o] = prior_mean[o];
+  mll_prepare_y_kernel<<<m, 256, 0, stream>>>(yt, y, ldy, n, npad, hp0);
+  BO_LAUNCH_CHECK("mll_prepare_y_kernel");
+
+  const size_t solve_smem = (size_t)(npad + 64 + 8) * sizeof(double);
+  static size_t attr_smem = 0;
+  if (solve_smem > attr_smem) {
+    BO_CUDA(cudaFuncSetAttribute(mll_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    attr_smem = solve_smem;
+  }
+  const long long strideA = (long long)npad * npad, strideD = (long long)npad * 64;
+  for (int s0 = 0; s0 < n_settings; s0 += gs) {
+    const int g = (n_settings - s0 < gs) ? (n_settings - s0) : gs;
+    for (int s = 0; s < g; ++s) {
+      ObjParams hp = hp0;
+      for (int o = 0; o < m; ++o) {
+        const double ls = length_scales[(long long)(s0 + s) * m + o];
+        hp.prior_var[o] = 1.0;
+        hp.neg_half_inv_ls2[o] = -0.5 / (ls * ls);
+      }
+      int rc = gram(A + (long long)s * m * strideA, npad, strideA, x, ldx, 0, n, npad, d, m, hp, jitter[s0 + s],
+                    stream);
+      if (rc) return rc;
+    }
+    BO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * g * m, stream));
+    int rc = cholesky_blocked(A, npad, strideA, npad, g * m, D, strideD, info, stream);
+    if (rc) return rc;
+    mll_solve_kernel<<<g * m, 256, solve_smem, stream>>>(vals + (long long)s0 * m, A, npad, strideA, D, strideD, info,
+                                                         yt, n, npad, m);
+    BO_LAUNCH_CHECK("mll_solve_kernel");
+  }
+  mll_sum_kernel<<<(n_settings + 127) / 128, 128, 0, stream>>>(out, vals, n_settings, m);
+  BO_LAUNCH_CHECK("mll_sum_kernel");
+  BO_CUDA(cudaStreamSynchronize(stream));
+  return BO_OK;
+}
+
+}  // namespace bo

@@ -1,0 +1,410 @@
+// score.cu -- the per-candidate hot path: K* -> mean / variance -> standardise -> UCB -> sum-UCB.
+// Reference: update_k_star, update_mean, update_variance, standardize_objectives (numba_kernels.py:406-570),
+// update_ucb, update_hypervolume_improvement (acquisition.py:55-108).
+//
+// Candidates are processed in chunks of `chunk_tiles` x 128.  Per chunk, three kernels:
+//   1. kstar_pack_kernel   RBF cross kernel written ONCE as 16 KB tiles in DMMA B-fragment order (so K* is
+//                          generated with N exps per candidate-objective, not N * N/256), fused with the
+//                          posterior-mean dot product k*.alpha (warp-shuffle reduction).
+//   2. trmm_sumsq_kernel   V = W K* on FP64 tensor cores (DMMA.8x8x4), W tiles and K* tiles streamed by
+//                          cp.async.bulk (UBLKCP) through a 4-stage mbarrier ring; V never leaves registers:
+//                          the epilogue reduces sum_i V[i,c]^2 per 128-row block with warp shuffles.
+//   3. finalize_kernel     var = max(var0 - sum, min_var), mu, standardise, UCB, acq; coalesced writes.
+// All reductions have a fixed order, so a candidate's result does not depend on the chunking or on how the
+// candidate set is sharded across GPUs (bit-identical top-k for any rank count).
+#include "score.cuh"
+
+namespace bo {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- K* tiles
+// B tile (kt, c): 16 k x 128 candidates -> [wn(4)][j(4)][sp(2)][lane(32)][q(2)]
+//   element = K*[kt*16 + (sp*2+q)*4 + t][c*128 + wn*32 + j*8 + g],  lane = g*4 + t
+// Warp w of the CTA owns columns wn = w>>1, j in {2*(w&1), 2*(w&1)+1} for ALL k, so the mean dot product
+// needs no cross-warp reduction.
+template <typename CT, int DMAX, int MOBJ>
+__global__ void __launch_bounds__(256, 2)
+    kstar_pack_kernel(double* __restrict__ Kp, double* __restrict__ meandot, const CT* __restrict__ cand, int ldc,
+                      long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk,
+                      const double* __restrict__ x, int ldx, int n, int npad, int d, const double* __restrict__ alpha,
+                      ObjParams hp) {
+  const int c = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wn = warp >> 1, j0 = (warp & 1) * 2;
+  const int nkt = npad / TK;
+
+  double cc[2][DMAX];
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    long long ci = cand0 + (long long)c * TN + wn * 32 + (j0 + jj) * 8 + g;
+    if (ci >= n_cand) ci = n_cand - 1;  // tail tile: computed, never stored by finalize
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) cc[jj][k] = (k < d) ? (double)cand[ci * ldc + k] : 0.0;
+  }
+  double macc[MOBJ][2];
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) macc[o][0] = macc[o][1] = 0.0;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      double val[MOBJ][2][2];  // [o][jj][q]
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = kt * TK + (sp * 2 + q) * 4 + t;
+        const bool live = e < n;
+        const int er = live ? e : 0;
+        double xe[DMAX];
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) xe[k] = (k < d) ? __ldg(x + (long long)er * ldx + k) : 0.0;
+        double al[MOBJ];
+#pragma unroll
+        for (int o = 0; o < MOBJ; ++o) al[o] = __ldg(alpha + (long long)o * npad + er);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          double sq = 0.0;
+#pragma unroll
+          for (int k = 0; k < DMAX; ++k) {
+            if (k < d) {
+              const double diff = xe[k] - cc[jj][k];
+              sq = fma(diff, diff, sq);
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < MOBJ; ++o) {
+            const double v = live ? hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]) : 0.0;
+            val[o][jj][q] = v;
+            macc[o][jj] = fma(v, al[o], macc[o][jj]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        double* tile = Kp + (((long long)o * chunk_tiles + c) * nkt + kt) * TILE_DOUBLES;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          double* dst = tile + ((wn * 4 + j0 + jj) * 2 + sp) * 64 + lane * 2;
+          *reinterpret_cast<double2*>(dst) = make_double2(val[o][jj][0], val[o][jj][1]);
+        }
+      }
+    }
+  }
+  // mean: reduce the 4 k-phases (t) of each column with warp shuffles
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      double s = macc[o][jj];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (t == 0) meandot[(long long)o * ld_chunk + (long long)c * TN + wn * 32 + (j0 + jj) * 8 + g] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- TRMM + sum of squares
+constexpr int TR_STAGES = 4;
+constexpr int TR_CONSUMER_WARPS = 8;  // 2 (rows) x 4 (candidates), warp tile 64 x 32
+constexpr int TR_THREADS = (TR_CONSUMER_WARPS + 1) * 32;
+constexpr size_t TR_SMEM = (size_t)TR_STAGES * 2 * TILE_DOUBLES * sizeof(double)  // A + B tiles
+                           + 2 * 2 * TN * sizeof(double)                           // epilogue exchange
+                           + 2 * TR_STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+    trmm_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const double* __restrict__ Wp,
+                      long long strideWp, const double* __restrict__ Kp, int nb, int chunk_tiles, int live_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sA = reinterpret_cast<double*>(smem_raw);
+  double* sB = sA + TR_STAGES * TILE_DOUBLES;
+  double* red = sB + TR_STAGES * TILE_DOUBLES;  // [2 buffers][2 wm][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 2 * TN);
+  uint64_t* empty = full + TR_STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = (nb + 1) / 2;
+  const int u = blockIdx.x;
+  // grid decode uses the live tile count of this chunk; the K* / part layouts use chunk_tiles
+  const int c = u % live_tiles;
+  const int pr = (u / live_tiles) % npairs;
+  const int o = u / (live_tiles * npairs);
+  const int nkt_total = nb * KT_PER_BLOCK;
+  const int ib_first = nb - 1 - pr;  // heavy block first, its light partner second: nb + 1 k-blocks per CTA
+  const int n_rb = (pr == ib_first) ? 1 : 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TR_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TR_CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const double* Wo = Wp + (long long)o * strideWp;
+  const double* Bo = Kp + ((long long)o * chunk_tiles + c) * nkt_total * TILE_DOUBLES;
+
+  if (warp == TR_CONSUMER_WARPS) {
+    // ===== producer: one lane streams tiles with the bulk-copy engine =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int rb = 0; rb < n_rb; ++rb) {
+        const int ib = rb == 0 ? ib_first : pr;
+        const int nkt = (ib + 1) * KT_PER_BLOCK;
+        const double* At = Wo + wpack_tile_offset(ib) * TILE_DOUBLES;
+        for (int kt = 0; kt < nkt; ++kt) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], 2 * TILE_DOUBLES * sizeof(double));
+          bulk_g2s(sA + stage * TILE_DOUBLES, At + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
+                   &full[stage]);
+          bulk_g2s(sB + stage * TILE_DOUBLES, Bo + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
+                   &full[stage]);
+          if (++stage == TR_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t = lane & 3;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int rb = 0; rb < n_rb; ++rb) {
+    const int ib = rb == 0 ? ib_first : pr;
+    const int nkt = (ib + 1) * KT_PER_BLOCK;
+    // k-tiles at or beyond this one only meet zeros of the lower-triangular W in this warp's 64 rows
+    const int kt_skip = (ib * TM + wm * 64 + 64) / TK;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < nkt; ++kt) {
+      mbar_wait(&full[stage], phase);
+      if (kt < kt_skip) {
+        const double* a_base = sA + stage * TILE_DOUBLES + wm * 1024 + lane * 2;
+        const double* b_base = sB + stage * TILE_DOUBLES + wn * 512 + lane * 2;
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+          double2 a[8], b[4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = lds128(a_base + (i * 2 + sp) * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == TR_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+
+    // epilogue: sum over this warp's 64 rows of V^2, per candidate column
+    double* rbuf = red + rb * 2 * TN;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fma(acc[i][j][r], acc[i][j][r], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (g == 0) rbuf[wm * TN + wn * 32 + j * 8 + 2 * t + r] = s;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // consumer warps only
+    if (threadIdx.x < TN)
+      part[((long long)o * nb + ib) * ld_chunk + (long long)c * TN + threadIdx.x] =
+          rbuf[threadIdx.x] + rbuf[TN + threadIdx.x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- finalize
+__global__ void finalize_kernel(double* __restrict__ mu_out, double* __restrict__ var_out,
+                                double* __restrict__ smu_out, double* __restrict__ svar_out,
+                                double* __restrict__ ucb_out, double* __restrict__ acq_out, long long ld_out,
+                                long long cand0, long long n_cand, const double* __restrict__ part,
+                                const double* __restrict__ meandot, long long ld_chunk, int chunk_cands, int nb, int m,
+                                ObjParams hp, double min_variance) {
+  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gi = cand0 + li;
+  if (li >= chunk_cands || gi >= n_cand) return;
+  double acq = 0.0;  // sequential sum from 0.0 (acquisition.py:108)
+  for (int o = 0; o < m; ++o) {
+    double q = 0.0;
+    for (int ib = 0; ib < nb; ++ib) q += part[((long long)o * nb + ib) * ld_chunk + li];
+    const double var = fmax(hp.prior_var[o] - q, min_variance);               // numba_kernels.py:532-535
+    const double mu = hp.prior_mean[o] + meandot[(long long)o * ld_chunk + li];  // :486-488
+    const double smu = (mu - hp.prior_mean[o]) / sqrt(hp.prior_var[o]);       // :563-565
+    const double svar = var / hp.prior_var[o];                                // :568-570
+    const double ucb = smu + hp.beta[o] * sqrt(fabs(svar));                   // acquisition.py:52
+    acq = acq + ucb;
+    if (mu_out) mu_out[o * ld_out + gi] = mu;
+    if (var_out) var_out[o * ld_out + gi] = var;
+    if (smu_out) smu_out[o * ld_out + gi] = smu;
+    if (svar_out) svar_out[o * ld_out + gi] = svar;
+    if (ucb_out) ucb_out[o * ld_out + gi] = ucb;
+  }
+  if (acq_out) acq_out[gi] = acq;
+}
+
+// stand-alone a6..a8 on existing arrays (HBM bound: reads 2m, writes up to 3m+1 doubles per candidate)
+__global__ void acquisition_kernel(double* __restrict__ smu_out, double* __restrict__ svar_out,
+                                   double* __restrict__ ucb_out, double* __restrict__ acq_out,
+                                   const double* __restrict__ mu_in, const double* __restrict__ var_in, long long ld,
+                                   long long n_cand, int m, ObjParams hp) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += stride) {
+    double acq = 0.0;
+    for (int o = 0; o < m; ++o) {
+      const double smu = (mu_in[o * ld + i] - hp.prior_mean[o]) / sqrt(hp.prior_var[o]);
+      const double svar = var_in[o * ld + i] / hp.prior_var[o];
+      const double ucb = smu + hp.beta[o] * sqrt(fabs(svar));
+      acq = acq + ucb;
+      if (smu_out) smu_out[o * ld + i] = smu;
+      if (svar_out) svar_out[o * ld + i] = svar;
+      if (ucb_out) ucb_out[o * ld + i] = ucb;
+    }
+    if (acq_out) acq_out[i] = acq;
+  }
+}
+
+template <typename CT, int DMAX>
+int launch_kstar_m(int m, dim3 grid, cudaStream_t st, double* Kp, double* meandot, const CT* cand, int ldc,
+                   long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x, int ldx,
+                   int n, int npad, int d, const double* alpha, const ObjParams& hp) {
+#define BO_KS(MO)                                                                                              \
+  kstar_pack_kernel<CT, DMAX, MO><<<grid, 256, 0, st>>>(Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles,    \
+                                                        ld_chunk, x, ldx, n, npad, d, alpha, hp)
+  switch (m) {
+    case 1: BO_KS(1); break;
+    case 2: BO_KS(2); break;
+    case 3: BO_KS(3); break;
+    default: BO_KS(4); break;
+  }
+#undef BO_KS
+  BO_LAUNCH_CHECK("kstar_pack_kernel");
+  return BO_OK;
+}
+
+template <typename CT>
+int launch_kstar(int m, int d, dim3 grid, cudaStream_t st, double* Kp, double* meandot, const CT* cand, int ldc,
+                 long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x, int ldx,
+                 int n, int npad, const double* alpha, const ObjParams& hp) {
+  if (d <= 4)
+    return launch_kstar_m<CT, 4>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
+                                 npad, d, alpha, hp);
+  if (d <= 8)
+    return launch_kstar_m<CT, 8>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
+                                 npad, d, alpha, hp);
+  return launch_kstar_m<CT, 16>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
+                                npad, d, alpha, hp);
+}
+
+}  // namespace
+
+// =========================================================================================== host driver
+ScorePlan make_score_plan(int n, int m, long long n_cand) {
+  ScorePlan p;
+  p.npad = round_up(n, TM);
+  p.nb = p.npad / TM;
+  const long long tiles = (n_cand + TN - 1) / TN;
+  // two CTAs' worth of tiles per SM per (objective, row pair): every wave of the TRMM grid is full
+  long long ct = 2LL * device_sm_count();
+  // cap the K* staging buffer near 3 GB
+  const long long bytes_per_tile = (long long)m * p.npad * TN * sizeof(double);
+  const long long cap = (3LL << 30) / bytes_per_tile;
+  if (ct > cap) ct = cap < 1 ? 1 : cap;
+  if (ct > tiles) ct = tiles;
+  if (ct < 1) ct = 1;
+  p.chunk_tiles = (int)ct;
+  p.ld_chunk = ct * TN;
+  p.kp_doubles = (size_t)m * ct * p.npad * TN;
+  p.part_doubles = (size_t)m * p.nb * p.ld_chunk;
+  p.mean_doubles = (size_t)m * p.ld_chunk;
+  return p;
+}
+
+size_t score_workspace_bytes(const ScorePlan& p) {
+  return align256(p.kp_doubles * 8) + align256(p.part_doubles * 8) + align256(p.mean_doubles * 8);
+}
+
+int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, int ldc, long long n_cand,
+                     const double* x, int ldx, int n, int d, int m, const double* wpack, const double* alpha,
+                     const ObjParams& hp, double min_variance, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  const ScorePlan p = make_score_plan(n, m, n_cand);
+  if (workspace_bytes < score_workspace_bytes(p)) {
+    set_error("score workspace too small: %zu < %zu", workspace_bytes, score_workspace_bytes(p));
+    return BO_ERR_WORKSPACE;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    BO_CUDA(cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
+    attr_set = true;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  double* Kp = reinterpret_cast<double*>(ws);
+  double* part = reinterpret_cast<double*>(ws + align256(p.kp_doubles * 8));
+  double* meandot = reinterpret_cast<double*>(ws + align256(p.kp_doubles * 8) + align256(p.part_doubles * 8));
+  const long long strideWp = (long long)wpack_tile_offset(p.nb) * TILE_DOUBLES;
+  const int npairs = (p.nb + 1) / 2;
+
+  for (long long cand0 = 0; cand0 < n_cand; cand0 += p.ld_chunk) {
+    const long long remaining = n_cand - cand0;
+    const int tiles = (int)((remaining < p.ld_chunk ? remaining : p.ld_chunk) + TN - 1) / TN;
+    int rc;
+    if (cand_kind == BO_CAND_I64)
+      rc = launch_kstar<long long>(m, d, dim3(tiles), stream, Kp, meandot, static_cast<const long long*>(cand), ldc,
+                                   cand0, n_cand, p.chunk_tiles, p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
+    else
+      rc = launch_kstar<double>(m, d, dim3(tiles), stream, Kp, meandot, static_cast<const double*>(cand), ldc, cand0,
+                                n_cand, p.chunk_tiles, p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
+    if (rc) return rc;
+    // grid: candidate tile fastest so that concurrently resident CTAs stream the same W tiles (L2 hits)
+    const unsigned grid = (unsigned)(m * npairs) * (unsigned)tiles;
+    trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp, p.nb,
+                                                             p.chunk_tiles, tiles);
+    BO_LAUNCH_CHECK("trmm_sumsq_kernel");
+    const int chunk_cands = tiles * TN;
+    finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(
+        out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld, cand0, n_cand, part, meandot, p.ld_chunk,
+        chunk_cands, p.nb, m, hp, min_variance);
+    BO_LAUNCH_CHECK("finalize_kernel");
+  }
+  return BO_OK;
+}
+
+int acquisition_only(double* smu, double* svar, double* ucb, double* acq, const double* mu, const double* var,
+                     long long ld, long long n_cand, int m, const ObjParams& hp, cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  long long blocks = (n_cand + 255) / 256;
+  const long long cap = 8LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  acquisition_kernel<<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, acq, mu, var, ld, n_cand, m, hp);
+  BO_LAUNCH_CHECK("acquisition_kernel");
+  return BO_OK;
+}
+
+}  // namespace bo

@@ -1,0 +1,344 @@
+// select.cu -- batch selection, Pareto filtering and exact hypervolume improvement.
+//   topk_slice_kernel   per-CTA top-k of an 8192-element slice by repeated block arg-max with the total order
+//                       (value desc, index asc, NaN last); applied level by level until one CTA remains.
+//                       Replaces the full argsort of select_next_batch (acquisition.py:134).
+//   match_rows_kernel   "candidate == some evaluated row" test of acquisition.py:139 for the few listed rows.
+//   pareto_kernel       tiled O(n * nz) dominance test with warp-ballot early-out (pareto.py:27-45 semantics:
+//                       maximisation, duplicates kept, NaN rows neither dominate nor are dominated).
+//   hvi_kernel          exact 2-/3-objective hypervolume improvement against a front held in shared memory.
+#include "select.cuh"
+
+namespace bo {
+
+namespace {
+
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_PER_THREAD = 32;
+constexpr int SEL_SLICE = SEL_THREADS * SEL_PER_THREAD;
+
+struct Best {
+  unsigned long long key;
+  long long idx;
+  int owner;  // (tid << 5) | p, -1 = nothing left
+};
+
+__device__ __forceinline__ bool better(const Best& a, const Best& b) {
+  if (a.owner < 0) return false;
+  if (b.owner < 0) return true;
+  if (a.key != b.key) return a.key > b.key;
+  return a.idx < b.idx;
+}
+__device__ __forceinline__ Best shfl_best(const Best& v, int off) {
+  Best r;
+  r.key = __shfl_xor_sync(0xffffffffu, v.key, off);
+  r.idx = __shfl_xor_sync(0xffffffffu, v.idx, off);
+  r.owner = __shfl_xor_sync(0xffffffffu, v.owner, off);
+  return r;
+}
+__device__ __forceinline__ double key_to_double(unsigned long long key) {
+  if (key == 0ull) return __longlong_as_double(0x7ff8000000000000ll);
+  const unsigned long long b = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+    topk_slice_kernel(double* __restrict__ out_val, long long* __restrict__ out_idx, const double* __restrict__ in_val,
+                      const long long* __restrict__ in_idx, long long n_in, int k, long long index_base) {
+  __shared__ Best warp_best[SEL_THREADS / 32];
+  __shared__ Best block_best;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long slice0 = (long long)blockIdx.x * SEL_SLICE;
+
+  unsigned long long keys[SEL_PER_THREAD];
+  long long idxs[SEL_PER_THREAD];
+  unsigned valid = 0u;
+#pragma unroll
+  for (int p = 0; p < SEL_PER_THREAD; ++p) {
+    const long long e = slice0 + (long long)p * SEL_THREADS + tid;
+    keys[p] = 0ull;
+    idxs[p] = -1;
+    if (e < n_in) {
+      const long long id = in_idx ? in_idx[e] : index_base + e;
+      if (id >= 0) {
+        keys[p] = order_key(in_val[e]);
+        idxs[p] = id;
+        valid |= 1u << p;
+      }
+    }
+  }
+  auto local_best = [&]() {
+    Best b;
+    b.key = 0ull; b.idx = 0; b.owner = -1;
+#pragma unroll
+    for (int p = 0; p < SEL_PER_THREAD; ++p) {
+      if (valid & (1u << p)) {
+        Best c;
+        c.key = keys[p]; c.idx = idxs[p]; c.owner = (tid << 5) | p;
+        if (better(c, b)) b = c;
+      }
+    }
+    return b;
+  };
+  Best mine = local_best();
+  for (int r = 0; r < k; ++r) {
+    Best b = mine;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const Best o = shfl_best(b, off);
+      if (better(o, b)) b = o;
+    }
+    if (lane == 0) warp_best[warp] = b;
+    __syncthreads();
+    if (warp == 0) {
+      Best c;
+      c.key = 0ull; c.idx = 0; c.owner = -1;
+      if (lane < SEL_THREADS / 32) c = warp_best[lane];
+#pragma unroll
+      for (int off = 4; off; off >>= 1) {
+        const Best o = shfl_best(c, off);
+        if (better(o, c)) c = o;
+      }
+      if (lane == 0) block_best = c;
+    }
+    __syncthreads();
+    const Best win = block_best;
+    if (tid == 0) {
+      const long long slot = (long long)blockIdx.x * k + r;
+      if (win.owner >= 0) {
+        out_val[slot] = key_to_double(win.key);
+        out_idx[slot] = win.idx;
+      } else {
+        out_val[slot] = __longlong_as_double(0x7ff8000000000000ll);
+        out_idx[slot] = -1;  // fewer than k elements in this slice
+      }
+    }
+    if (win.owner >= 0 && (win.owner >> 5) == tid) {
+      valid &= ~(1u << (win.owner & 31));
+      mine = local_best();
+    }
+    // block_best is rewritten only after the next __syncthreads pair, so no extra barrier is needed here
+  }
+}
+
+template <typename CT>
+__global__ void match_rows_kernel(uint8_t* __restrict__ flag, const long long* __restrict__ idx, long long index_base,
+                                  const CT* __restrict__ cand, int ldc, const double* __restrict__ x, int ldx, int n,
+                                  int d) {
+  __shared__ int hit;
+  if (threadIdx.x == 0) hit = 0;
+  __syncthreads();
+  const long long id = idx[blockIdx.x];
+  if (id >= 0) {
+    const CT* row = cand + (id - index_base) * ldc;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      bool same = true;
+      for (int k = 0; k < d; ++k) same = same && ((double)row[k] == x[(long long)e * ldx + k]);
+      if (same) hit = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag[blockIdx.x] = (uint8_t)hit;
+}
+
+// ------------------------------------------------------------------------------------------- Pareto
+constexpr int PAR_TILE = 1024;
+
+template <int MOBJ>
+__global__ void __launch_bounds__(256)
+    pareto_kernel(uint8_t* __restrict__ mask, const double* __restrict__ y, long long ldy, long long n,
+                  const double* __restrict__ z, long long ldz, long long nz) {
+  __shared__ double zs[MOBJ][PAR_TILE];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double yi[MOBJ];
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) yi[o] = (i < n) ? y[i * ldy + o] : 0.0;
+  bool dominated = (i >= n);  // out-of-range lanes count as done for the early-out votes
+  for (long long j0 = 0; j0 < nz; j0 += PAR_TILE) {
+    const int cnt = (int)((nz - j0 < PAR_TILE) ? (nz - j0) : PAR_TILE);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) zs[o][e] = z[(j0 + e) * ldz + o];
+    }
+    __syncthreads();
+    // warp-ballot early-out: a warp whose 32 points are all already dominated skips the tile
+    if (__ballot_sync(0xffffffffu, !dominated) != 0u) {
+      for (int j = 0; j < cnt; ++j) {
+        bool ge = true, gt = false;
+#pragma unroll
+        for (int o = 0; o < MOBJ; ++o) {
+          const double zj = zs[o][j];  // broadcast read
+          ge = ge && (zj >= yi[o]);
+          gt = gt || (zj > yi[o]);
+        }
+        dominated = dominated || (ge && gt);
+      }
+    }
+    if (__syncthreads_and(dominated ? 1 : 0)) break;
+  }
+  if (i < n) mask[i] = dominated ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------- exact HVI
+constexpr int HVI_MAX_FRONT = 1024;
+
+// front: (P, MOBJ) rows sorted by objective 0 DESCENDING.  For MOBJ == 3 slabs are cut at the front's
+// objective-2 levels; inside a slab the covered area of the box [ref, u] is the f0-descending sweep over the
+// points whose objective 2 reaches the slab.
+template <int MOBJ>
+__global__ void __launch_bounds__(256)
+    hvi_kernel(double* __restrict__ hvi, const double* __restrict__ ucb, long long ld, long long n_cand,
+               const double* __restrict__ front, int P, double r0, double r1, double r2) {
+  __shared__ double f0[HVI_MAX_FRONT], f1[HVI_MAX_FRONT], f2[HVI_MAX_FRONT], zlev[HVI_MAX_FRONT + 1];
+  __shared__ int rank2[HVI_MAX_FRONT];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    f0[p] = fmax(front[(long long)p * MOBJ + 0], r0);
+    f1[p] = fmax(front[(long long)p * MOBJ + 1], r1);
+    f2[p] = (MOBJ == 3) ? fmax(front[(long long)p * MOBJ + 2], r2) : 0.0;
+  }
+  __syncthreads();
+  if (MOBJ == 3) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      int r = 0;
+      for (int q = 0; q < P; ++q) r += (f2[q] > f2[p] || (f2[q] == f2[p] && q < p)) ? 1 : 0;
+      rank2[p] = r;
+      zlev[r] = f2[p];  // zlev[s] = s-th largest objective-2 value
+    }
+    if (threadIdx.x == 0) zlev[P] = r2;
+    __syncthreads();
+  }
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const double u0 = ucb[i], u1 = ucb[ld + i];
+  const double u2 = (MOBJ == 3) ? ucb[2 * ld + i] : 0.0;
+  const double w0 = u0 - r0, w1 = u1 - r1;
+  double total = 0.0;
+  if (w0 > 0.0 && w1 > 0.0 && (MOBJ == 2 || u2 > r2)) {
+    const double box = w0 * w1;
+    if (MOBJ == 2) {
+      double covered = 0.0, best1 = r1;
+      for (int p = 0; p < P; ++p) {
+        const double a0 = fmin(f0[p], u0), a1 = fmin(f1[p], u1);
+        if (a1 > best1) {
+          covered += (a0 - r0) * (a1 - best1);
+          best1 = a1;
+        }
+      }
+      total = box - covered;
+    } else {
+      // slab s: z in (zlev[s], z_hi], z_hi = +inf for s = 0 else zlev[s-1]; active points: rank2 < s
+      for (int s = 0; s <= P; ++s) {
+        const double z_hi = (s == 0) ? u2 : fmin(zlev[s - 1], u2);
+        const double z_lo = zlev[s];
+        const double thick = z_hi - z_lo;
+        if (!(thick > 0.0)) continue;
+        double covered = 0.0, best1 = r1;
+        for (int p = 0; p < P; ++p) {
+          if (rank2[p] < s) {
+            const double a0 = fmin(f0[p], u0), a1 = fmin(f1[p], u1);
+            if (a1 > best1) {
+              covered += (a0 - r0) * (a1 - best1);
+              best1 = a1;
+            }
+          }
+        }
+        total += thick * (box - covered);
+      }
+    }
+  }
+  hvi[i] = total;
+}
+
+}  // namespace
+
+// =========================================================================================== host drivers
+size_t topk_workspace_bytes(long long n_cand, int k) {
+  const long long blocks0 = (n_cand + SEL_SLICE - 1) / SEL_SLICE;
+  const size_t pairs = (size_t)(blocks0 > 0 ? blocks0 : 1) * (size_t)k;
+  // two ping-pong (value, index) buffers
+  return 2 * (align256(pairs * sizeof(double)) + align256(pairs * sizeof(long long)));
+}
+
+int topk_levels(double* out_val, long long* out_idx, const double* val, const long long* idx, long long n_in, int k,
+                long long index_base, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < topk_workspace_bytes(n_in, k)) {
+    set_error("top-k workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  const long long blocks0 = (n_in + SEL_SLICE - 1) / SEL_SLICE;
+  const size_t pairs = (size_t)(blocks0 > 0 ? blocks0 : 1) * (size_t)k;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  double* v[2];
+  long long* ix[2];
+  size_t off = 0;
+  for (int b = 0; b < 2; ++b) {
+    v[b] = reinterpret_cast<double*>(ws + off);
+    off += align256(pairs * sizeof(double));
+    ix[b] = reinterpret_cast<long long*>(ws + off);
+    off += align256(pairs * sizeof(long long));
+  }
+  const double* cur_v = val;
+  const long long* cur_i = idx;
+  long long cur_n = n_in;
+  int buf = 0;
+  while (true) {
+    long long blocks = (cur_n + SEL_SLICE - 1) / SEL_SLICE;
+    if (blocks < 1) blocks = 1;
+    const bool last = blocks == 1;
+    double* ov = last ? out_val : v[buf];
+    long long* oi = last ? out_idx : ix[buf];
+    topk_slice_kernel<<<(unsigned)blocks, SEL_THREADS, 0, stream>>>(ov, oi, cur_v, cur_i, cur_n, k, index_base);
+    BO_LAUNCH_CHECK("topk_slice_kernel");
+    if (last) break;
+    cur_v = ov;
+    cur_i = oi;
+    cur_n = blocks * k;
+    buf ^= 1;
+  }
+  return BO_OK;
+}
+
+int match_rows(uint8_t* flag, const long long* idx, int n_idx, long long index_base, const void* cand, int cand_kind,
+               int ldc, const double* x, int ldx, int n, int d, cudaStream_t stream) {
+  if (n_idx <= 0) return BO_OK;
+  if (cand_kind == BO_CAND_I64)
+    match_rows_kernel<long long><<<n_idx, 128, 0, stream>>>(flag, idx, index_base,
+                                                            static_cast<const long long*>(cand), ldc, x, ldx, n, d);
+  else
+    match_rows_kernel<double><<<n_idx, 128, 0, stream>>>(flag, idx, index_base, static_cast<const double*>(cand),
+                                                         ldc, x, ldx, n, d);
+  BO_LAUNCH_CHECK("match_rows_kernel");
+  return BO_OK;
+}
+
+int pareto_mask(uint8_t* mask, const double* y, long long ldy, long long n, const double* z, long long ldz,
+                long long nz, int m, cudaStream_t stream) {
+  if (n <= 0) return BO_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  switch (m) {
+    case 1: pareto_kernel<1><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
+    case 2: pareto_kernel<2><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
+    case 3: pareto_kernel<3><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
+    default: pareto_kernel<4><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
+  }
+  BO_LAUNCH_CHECK("pareto_kernel");
+  return BO_OK;
+}
+
+int hvi(double* out, const double* ucb, long long ld, long long n_cand, int m, const double* front, int n_front,
+        const double* ref, cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  if (n_front > HVI_MAX_FRONT) {
+    set_error("front larger than %d points", HVI_MAX_FRONT);
+    return BO_ERR_INVALID;
+  }
+  const unsigned grid = (unsigned)((n_cand + 255) / 256);
+  if (m == 2)
+    hvi_kernel<2><<<grid, 256, 0, stream>>>(out, ucb, ld, n_cand, front, n_front, ref[0], ref[1], 0.0);
+  else
+    hvi_kernel<3><<<grid, 256, 0, stream>>>(out, ucb, ld, n_cand, front, n_front, ref[0], ref[1], ref[2]);
+  BO_LAUNCH_CHECK("hvi_kernel");
+  return BO_OK;
+}
+
+}  // namespace bo

@@ -1,0 +1,223 @@
+"""Device-resident GP scorer: the fused form of the reference's per-iteration hot path.
+
+``DeviceGP.fit``    = update_k + invert_k (+ the Kinv @ dy half of update_mean)
+                      (reference bayesian_optimization.py:129-142)
+``DeviceGP.score``  = update_k_star + update_mean + update_variance + standardize_objectives
+                      + update_ucb + update_hypervolume_improvement (:145-199)
+``DeviceGP.select`` = select_next_batch (:202-207)
+
+PyTorch is used only for plumbing (device memory, pinned staging buffers, streams); every
+arithmetic step is a kernel of libbo_b200.so reached through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import KERNEL_JITTER, MIN_VARIANCE
+
+_F64 = torch.float64
+
+
+def require_cuda() -> torch.device:
+    """The package is GPU-only: fail loudly instead of falling back to the CPU."""
+    if not torch.cuda.is_available():
+        raise _lib.BoError("bayesopt_smart_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Workspace:
+    """Grow-only device scratch buffers, one per purpose."""
+
+    def __init__(self):
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, key: str, nbytes: int, device) -> torch.Tensor:
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+def to_device(a, dtype=None, device=None) -> torch.Tensor:
+    """numpy / torch -> contiguous CUDA tensor (pinned staging for host arrays)."""
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device, dtype=dtype or a.dtype)
+        return t.contiguous()
+    arr = np.ascontiguousarray(a)
+    if dtype is not None:
+        arr = arr.astype({torch.float64: np.float64, torch.int64: np.int64}[dtype], copy=False)
+    t = torch.from_numpy(arr)
+    try:
+        t = t.pin_memory()
+    except RuntimeError:
+        pass
+    return t.to(device, non_blocking=True)
+
+
+def candidate_kind(cand: torch.Tensor) -> int:
+    if cand.dtype == torch.float64:
+        return _lib.BO_CAND_F64
+    if cand.dtype == torch.int64:
+        return _lib.BO_CAND_I64
+    raise TypeError(f"candidates must be float64 or int64, got {cand.dtype}")
+
+
+class DeviceGP:
+    """GP factor + scorer living in HBM.  One instance per process / GPU."""
+
+    def __init__(self, device=None):
+        self.device = device or require_cuda()
+        self.lib = _lib.load()
+        self.ws = _Workspace()
+        self.n = 0
+        self.d = 0
+        self.m = 0
+        self.x: Optional[torch.Tensor] = None
+        self.wpack: Optional[torch.Tensor] = None
+        self.alpha: Optional[torch.Tensor] = None
+        self.prior_mean = self.prior_variance = self.length_scales = None
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, x_vector, y_vector, prior_mean, prior_variance, length_scales, current_eval: int,
+            jitter: float = KERNEL_JITTER) -> None:
+        """Factor K + jitter I for the first ``current_eval`` rows.  Raises numpy LinAlgError if not PD."""
+        n = int(current_eval)
+        x = to_device(x_vector, _F64, self.device)
+        y = to_device(y_vector, _F64, self.device)
+        if x.dim() != 2 or y.dim() != 2 or x.shape[0] < n or y.shape[0] < n:
+            raise ValueError("x_vector (T,d) and y_vector (T,m) must hold at least current_eval rows")
+        d, m = x.shape[1], y.shape[1]
+        npad = self.lib.bo_npad(n)
+        self.wpack = torch.empty(m * self.lib.bo_wpack_doubles(n), dtype=_F64, device=self.device)
+        self.alpha = torch.empty(m * npad, dtype=_F64, device=self.device)
+        ws_bytes = self.lib.bo_fit_workspace_bytes(n, m)
+        ws = self.ws.get("fit", ws_bytes, self.device)
+        self._mean_h, pm = _lib.host_doubles(prior_mean, m)
+        self._var_h, pv = _lib.host_doubles(prior_variance, m)
+        self._ls_h, pl = _lib.host_doubles(length_scales, m)
+        _lib.check(self.lib.bo_gp_fit_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
+                                          y.stride(0), n, d, m, pm, pv, pl, float(jitter), _ptr(ws), ws_bytes,
+                                          _stream()))
+        self.x, self.n, self.d, self.m = x, n, d, m
+        self.prior_mean = self._mean_h.copy()
+        self.prior_variance = self._var_h.copy()
+        self.length_scales = self._ls_h.copy()
+
+    # ------------------------------------------------------------------ score
+    def score(self, candidates, betas, *, want=("mu", "var", "acq"), out: Optional[Dict[str, torch.Tensor]] = None,
+              min_variance: float = MIN_VARIANCE) -> Dict[str, torch.Tensor]:
+        """Posterior + UCB + sum-UCB for every candidate row.  Returns CUDA tensors.
+
+        ``want`` picks which arrays are written: mu, var, std_mu, std_var, ucb (each (m, M)), acq (M,).
+        ``out`` may carry preallocated tensors under the same keys.
+        """
+        if self.wpack is None:
+            raise _lib.BoError("DeviceGP.score called before fit")
+        cand = to_device(candidates, None, self.device)
+        if cand.dim() != 2 or cand.shape[1] != self.d:
+            raise ValueError(f"candidates must be (M, {self.d})")
+        kind = candidate_kind(cand)
+        n_cand = cand.shape[0]
+        m = self.m
+        res: Dict[str, Optional[torch.Tensor]] = {}
+        for key in ("mu", "var", "std_mu", "std_var", "ucb", "acq"):
+            if out is not None and key in out:
+                res[key] = out[key]
+            elif key in want:
+                shape = (n_cand,) if key == "acq" else (m, n_cand)
+                res[key] = torch.empty(shape, dtype=_F64, device=self.device)
+            else:
+                res[key] = None
+        ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
+        ws = self.ws.get("score", ws_bytes, self.device)
+        _, pm = _lib.host_doubles(self.prior_mean, m)
+        _, pv = _lib.host_doubles(self.prior_variance, m)
+        _, pl = _lib.host_doubles(self.length_scales, m)
+        bet, pb = _lib.host_doubles(betas, m)
+        _lib.check(self.lib.bo_score_f64(_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]), _ptr(res["std_var"]),
+                                         _ptr(res["ucb"]), _ptr(res["acq"]), n_cand, _ptr(cand), kind,
+                                         cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0), self.n, self.d, m,
+                                         _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl, pb, float(min_variance),
+                                         _ptr(ws), ws_bytes, _stream()))
+        return {k: v for k, v in res.items() if v is not None}
+
+    # ------------------------------------------------------------------ select
+    def topk(self, acq: torch.Tensor, k: int, index_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top-k (value desc, index asc, NaN last) of a device vector -> (values, indices) on device."""
+        n = acq.numel()
+        k = int(min(k, n, _lib.BO_MAX_TOPK))
+        vals = torch.empty(k, dtype=_F64, device=self.device)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        ws_bytes = self.lib.bo_topk_workspace_bytes(n, k)
+        ws = self.ws.get("topk", ws_bytes, self.device)
+        _lib.check(self.lib.bo_topk_f64(_ptr(vals), _ptr(idx), _ptr(acq), n, k, int(index_base), _ptr(ws), ws_bytes,
+                                        _stream()))
+        return vals, idx
+
+    def match_rows(self, idx: torch.Tensor, candidates: torch.Tensor, evaluated: torch.Tensor,
+                   index_base: int = 0) -> torch.Tensor:
+        """flag[i] = candidates[idx[i] - index_base] equals some row of ``evaluated`` (acquisition.py:139)."""
+        flags = torch.zeros(idx.numel(), dtype=torch.uint8, device=self.device)
+        n_ev = evaluated.shape[0]
+        _lib.check(self.lib.bo_match_rows_f64(_ptr(flags), _ptr(idx), idx.numel(), int(index_base), _ptr(candidates),
+                                              candidate_kind(candidates), candidates.stride(0),
+                                              _ptr(evaluated) if n_ev else None,
+                                              evaluated.stride(0) if n_ev else 1, n_ev, candidates.shape[1],
+                                              _stream()))
+        return flags
+
+    def select(self, candidates: torch.Tensor, acq: torch.Tensor, evaluated: torch.Tensor, batch_size: int,
+               index_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """select_next_batch on device (reference acquisition.py:116-144).
+
+        Takes the top-(batch+slack) scores, drops rows that equal an evaluated point, keeps the first
+        ``batch_size``; the slack grows until enough rows survive or the candidates are exhausted.
+        Returns (values, global indices) as host arrays, best first.
+        """
+        n = acq.numel()
+        k = min(n, batch_size + 16)
+        while True:
+            vals, idx = self.topk(acq, k, index_base)
+            flags = self.match_rows(idx, candidates, evaluated, index_base)
+            v = vals.cpu().numpy()
+            i = idx.cpu().numpy()
+            keep = (flags.cpu().numpy() == 0) & (i >= 0)
+            if keep.sum() >= batch_size or k >= min(n, _lib.BO_MAX_TOPK):
+                return v[keep][:batch_size], i[keep][:batch_size]
+            k = min(n, _lib.BO_MAX_TOPK, k * 4)
+
+    def topk_merge(self, vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Global top-k of gathered (value, index) pairs with the same total order (after an all-gather)."""
+        n_pairs = vals.numel()
+        k = int(min(k, n_pairs, _lib.BO_MAX_TOPK))
+        ov = torch.empty(k, dtype=_F64, device=self.device)
+        oi = torch.empty(k, dtype=torch.int64, device=self.device)
+        ws_bytes = self.lib.bo_topk_workspace_bytes(n_pairs, k)
+        ws = self.ws.get("topk", ws_bytes, self.device)
+        _lib.check(self.lib.bo_topk_merge_f64(_ptr(ov), _ptr(oi), _ptr(vals.contiguous()), _ptr(idx.contiguous()),
+                                              n_pairs, k, _ptr(ws), ws_bytes, _stream()))
+        return ov, oi
+
+
+def device_info() -> dict:
+    lib = _lib.load()
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    l2, hbm = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(lib.bo_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr), ctypes.byref(l2),
+                                  ctypes.byref(hbm)))
+    return dict(sm_count=sm.value, cc=(maj.value, mnr.value), l2_bytes=l2.value, hbm_bytes=hbm.value)

@@ -1,0 +1,266 @@
+"""Drop-in for the reference's ``bayesopt/numba_kernels.py`` -- same function names, parameter
+names/order, in-place semantics and return values -- with every array operation executed by
+libbo_b200.so on the GPU (host buffers are copied in and out per call).
+
+The module keeps the reference's file name so that ``from bayesopt.numba_kernels import update_k``
+style imports can simply be re-pointed; nothing here uses Numba.  The fused, device-resident form
+of the same sequence is :class:`bayesopt_smart_b200.engine.DeviceGP`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from . import _lib
+from .config import (
+    CHOLESKY_JITTER,
+    HYPERPARAM_FTOL,
+    HYPERPARAM_MAXITER,
+    HYPERPARAM_METHOD,
+    HYPERPARAM_MIN_BOUND,
+    HYPERPARAM_XTOL,
+    KERNEL_JITTER,
+    MIN_VARIANCE,
+    NUMBA_FLOAT_TYPE,
+)
+from .engine import _Workspace, _ptr, _stream, candidate_kind, require_cuda, to_device
+
+_F64 = torch.float64
+_ws = _Workspace()
+
+
+# =============================================================================
+# INITIALIZATION / PRIORS (host NumPy: O(initial_samples), runs once)
+# =============================================================================
+
+
+def initialize_lhs_integer(x_vector, y_vector, bounds, function, n_samples=8):
+    """Integer Latin-hypercube initialisation.  Reference numba_kernels.py:50-95.
+
+    Unlike the reference (which calls ``function`` inside nopython code) any Python callable works.
+    """
+    bounds = np.asarray(bounds)
+    dim = len(bounds)
+    samples = np.empty((n_samples, dim), dtype=NUMBA_FLOAT_TYPE)
+    for d in range(dim):
+        perm = np.random.permutation(n_samples)
+        min_val, max_val = bounds[d, 0], bounds[d, 1]
+        step = (max_val - min_val) / n_samples
+        for i in range(n_samples):
+            low = min_val + perm[i] * step
+            high = min_val + (perm[i] + 1) * step
+            sample_val = int(np.random.uniform(low, high))
+            samples[i, d] = min(sample_val, max_val - 1)
+    for i in range(n_samples):
+        x_vector[i] = samples[i]
+        y_vector[i] = function(x_vector[i])
+    return n_samples
+
+
+def compute_prior_mean(y_vector, n_evaluations, n_objectives):
+    """Reference numba_kernels.py:103-122."""
+    return np.array([np.mean(y_vector[:n_evaluations, o]) for o in range(n_objectives)], dtype=NUMBA_FLOAT_TYPE)
+
+
+def compute_prior_variance(y_vector, n_evaluations, n_objectives):
+    """Population variance per objective.  Reference numba_kernels.py:125-144."""
+    return np.array([np.var(y_vector[:n_evaluations, o]) for o in range(n_objectives)], dtype=NUMBA_FLOAT_TYPE)
+
+
+# =============================================================================
+# MARGINAL LOG LIKELIHOOD
+# =============================================================================
+
+
+def mll_batched(x_vector, y_vector, prior_mean, length_scales, jitters, current_eval):
+    """LML for S settings at once (cfg5).  ``length_scales`` is (S, m), ``jitters`` (S,).
+
+    Setting s with jitter CHOLESKY_JITTER equals ``compute_mll`` (numba_kernels.py:152-235).
+    Non-positive-definite settings give NaN.  Returns a (S,) float64 host array.
+    """
+    dev = require_cuda()
+    lib = _lib.load()
+    n = int(current_eval)
+    x = to_device(x_vector, _F64, dev)
+    y = to_device(y_vector, _F64, dev)
+    m = y.shape[1]
+    ls = np.ascontiguousarray(np.asarray(length_scales, dtype=np.float64).reshape(-1, m))
+    jit = np.ascontiguousarray(np.asarray(jitters, dtype=np.float64).reshape(-1))
+    s = ls.shape[0]
+    if jit.size != s:
+        raise ValueError("one jitter per setting")
+    out = torch.empty(s, dtype=_F64, device=dev)
+    ws_bytes = lib.bo_mll_workspace_bytes(n, m, s)
+    ws = _ws.get("mll", ws_bytes, dev)
+    _, pm = _lib.host_doubles(prior_mean, m)
+    _lib.check(lib.bo_mll_batched_f64(_ptr(out), _ptr(x), x.stride(0), _ptr(y), y.stride(0), n, x.shape[1], m, pm,
+                                      ls.ctypes.data_as(_lib._dp), jit.ctypes.data_as(_lib._dp), s, _ptr(ws),
+                                      ws_bytes, _stream()))
+    return out.cpu().numpy()
+
+
+def compute_mll(x_vector, y_vector, kernel_matrix, prior_mean, prior_variance, length_scales, current_eval):
+    """Log marginal likelihood summed over objectives.  Reference numba_kernels.py:152-235.
+
+    Keeps the reference's side effect of overwriting ``kernel_matrix`` (:178).  Raises
+    numpy.linalg.LinAlgError when the normalised Gram matrix is not positive definite.
+    """
+    update_k(kernel_matrix, x_vector, 0, current_eval, prior_variance, length_scales)
+    val = mll_batched(x_vector, y_vector, prior_mean, np.asarray(length_scales)[None, :], [CHOLESKY_JITTER],
+                      current_eval)[0]
+    if np.isnan(val):
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    return float(val)
+
+
+def optimize_hyperparams_mll(x_vector, y_vector, kernel_matrix, prior_mean, prior_variance, length_scales,
+                             current_eval):
+    """Powell search over (length_scales, prior_variance) maximising the MLL; updates both IN PLACE and
+    returns the SciPy result.  Reference numba_kernels.py:238-321 (Powell settings config.py:73-83).
+
+    The training set is uploaded once; each objective evaluation is one batched-MLL call with S = 1.
+    Deviation: ``kernel_matrix`` is not clobbered on every evaluation (the loop rebuilds it right after,
+    bayesian_optimization.py:129).
+    """
+    dev = require_cuda()
+    n_objectives = y_vector.shape[1]
+    x_dev = to_device(x_vector[:current_eval], _F64, dev)
+    y_dev = to_device(y_vector[:current_eval], _F64, dev)
+    initial_guess = np.concatenate([length_scales, prior_variance])
+    bounds = [(HYPERPARAM_MIN_BOUND, None)] * (2 * n_objectives)
+
+    def objective(params):
+        ls = np.asarray(params[:n_objectives], dtype=np.float64)
+        val = mll_batched(x_dev, y_dev, prior_mean, ls[None, :], [CHOLESKY_JITTER], current_eval)[0]
+        if np.isnan(val):
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        return -float(val)
+
+    optim_result = minimize(objective, initial_guess, method=HYPERPARAM_METHOD, bounds=bounds,
+                            options={"xtol": HYPERPARAM_XTOL, "ftol": HYPERPARAM_FTOL,
+                                     "maxiter": HYPERPARAM_MAXITER})
+    length_scales[:] = optim_result.x[:n_objectives]
+    prior_variance[:] = optim_result.x[n_objectives:]
+    return optim_result
+
+
+# =============================================================================
+# KERNEL MATRIX OPERATIONS
+# =============================================================================
+
+
+def update_k(kernel_matrix, x_vector, last_eval, current_eval, prior_variance, length_scales):
+    """RBF Gram matrix for rows/cols [last_eval, current_eval), in place.  Reference numba_kernels.py:329-367."""
+    dev = require_cuda()
+    lib = _lib.load()
+    m = kernel_matrix.shape[0]
+    n = int(current_eval)
+    if n <= last_eval:
+        return
+    x = to_device(np.asarray(x_vector)[:n], _F64, dev)
+    k_dev = torch.empty((m, n, n), dtype=_F64, device=dev)
+    _, pv = _lib.host_doubles(prior_variance, m)
+    _, pl = _lib.host_doubles(length_scales, m)
+    _lib.check(lib.bo_gram_f64(_ptr(k_dev), n, _ptr(x), x.stride(0), int(last_eval), n, x.shape[1], m, pv, pl,
+                               _stream()))
+    kernel_matrix[:, last_eval:n, last_eval:n] = k_dev[:, last_eval:, last_eval:].cpu().numpy()
+
+
+def invert_k(current_eval, kernel_matrix):
+    """``inv(K_o + 1e-6 I)`` per objective; allocates and returns (m, n, n).  Reference numba_kernels.py:370-403.
+
+    Computed on the GPU as ``W^T W`` with ``W = chol(K + jitter I)^-1``; raises numpy LinAlgError if not PD.
+    """
+    dev = require_cuda()
+    lib = _lib.load()
+    m = kernel_matrix.shape[0]
+    n = int(current_eval)
+    k_dev = to_device(np.ascontiguousarray(kernel_matrix[:, :n, :n]), _F64, dev)
+    out = torch.empty((m, n, n), dtype=_F64, device=dev)
+    ws_bytes = lib.bo_inverse_workspace_bytes(n, m)
+    ws = _ws.get("inverse", ws_bytes, dev)
+    _lib.check(lib.bo_inverse_f64(_ptr(out), _ptr(k_dev), n, n, m, float(KERNEL_JITTER), _ptr(ws), ws_bytes,
+                                  _stream()))
+    return out.cpu().numpy()
+
+
+def update_k_star(k_star, x_vector, input_space, last_eval, current_eval, prior_variance, length_scales):
+    """Cross kernel rows [last_eval, current_eval), in place.  Reference numba_kernels.py:406-442."""
+    dev = require_cuda()
+    lib = _lib.load()
+    m, _, n_cand = k_star.shape
+    n = int(current_eval)
+    rows = n - int(last_eval)
+    if rows <= 0:
+        return
+    x = to_device(np.asarray(x_vector)[:n], _F64, dev)
+    cand = to_device(input_space, None, dev)
+    ks = torch.empty((m, rows, n_cand), dtype=_F64, device=dev)
+    _, pv = _lib.host_doubles(prior_variance, m)
+    _, pl = _lib.host_doubles(length_scales, m)
+    # the device buffer holds only the requested rows: shift the row origin by last_eval
+    base = _ptr(ks) - int(last_eval) * n_cand * 8
+    _lib.check(lib.bo_kstar_dense_f64(base, n_cand, rows * n_cand, _ptr(x), x.stride(0), _ptr(cand),
+                                      candidate_kind(cand), cand.stride(0), n_cand, int(last_eval), n, x.shape[1], m,
+                                      pv, pl, _stream()))
+    k_star[:, last_eval:n, :] = ks.cpu().numpy()
+
+
+# =============================================================================
+# GAUSSIAN PROCESS PREDICTIONS
+# =============================================================================
+
+
+def update_mean(mu_objectives, k_star, inverted_kernel_matrix, y_vector, prior_mean, current_eval):
+    """Posterior mean, in place.  Reference numba_kernels.py:450-488."""
+    dev = require_cuda()
+    lib = _lib.load()
+    m, n_cand = mu_objectives.shape
+    n = int(current_eval)
+    ks = to_device(np.ascontiguousarray(k_star[:, :n, :]), _F64, dev)
+    kinv = to_device(np.ascontiguousarray(inverted_kernel_matrix[:, :n, :n]), _F64, dev)
+    y = to_device(np.asarray(y_vector)[:n], _F64, dev)
+    mu = torch.empty((m, n_cand), dtype=_F64, device=dev)
+    ws_bytes = lib.bo_dense_workspace_bytes(n, n_cand)
+    ws = _ws.get("dense", ws_bytes, dev)
+    _, pm = _lib.host_doubles(prior_mean, m)
+    _lib.check(lib.bo_mean_dense_f64(_ptr(mu), n_cand, _ptr(ks), n_cand, n * n_cand, _ptr(kinv), n, n * n, _ptr(y),
+                                     y.stride(0), pm, n, n_cand, m, _ptr(ws), ws_bytes, _stream()))
+    mu_objectives[:, :] = mu.cpu().numpy()
+
+
+def update_variance(variance_objectives, k_star, inverted_kernel_matrix, prior_variance, current_eval):
+    """Posterior variance clamped at MIN_VARIANCE, in place.  Reference numba_kernels.py:491-535."""
+    dev = require_cuda()
+    lib = _lib.load()
+    m, n_cand = variance_objectives.shape
+    n = int(current_eval)
+    ks = to_device(np.ascontiguousarray(k_star[:, :n, :]), _F64, dev)
+    kinv = to_device(np.ascontiguousarray(inverted_kernel_matrix[:, :n, :n]), _F64, dev)
+    var = torch.empty((m, n_cand), dtype=_F64, device=dev)
+    ws_bytes = lib.bo_dense_workspace_bytes(n, n_cand)
+    ws = _ws.get("dense", ws_bytes, dev)
+    _, pv = _lib.host_doubles(prior_variance, m)
+    _lib.check(lib.bo_variance_dense_f64(_ptr(var), n_cand, _ptr(ks), n_cand, n * n_cand, _ptr(kinv), n, n * n, pv,
+                                         float(MIN_VARIANCE), n, n_cand, m, _ptr(ws), ws_bytes, _stream()))
+    variance_objectives[:, :] = var.cpu().numpy()
+
+
+def standardize_objectives(std_mu_objectives, std_variance_objectives, mu_objectives, variance_objectives,
+                           prior_mean, prior_variance):
+    """(mu - mu0)/sqrt(var0), var/var0, in place.  Reference numba_kernels.py:538-570."""
+    dev = require_cuda()
+    lib = _lib.load()
+    m, n_cand = mu_objectives.shape
+    mu = to_device(mu_objectives, _F64, dev)
+    var = to_device(variance_objectives, _F64, dev)
+    smu = torch.empty_like(mu)
+    svar = torch.empty_like(var)
+    _, pm = _lib.host_doubles(prior_mean, m)
+    _, pv = _lib.host_doubles(prior_variance, m)
+    _, pb = _lib.host_doubles(np.zeros(m), m)
+    _lib.check(lib.bo_acquisition_f64(_ptr(smu), _ptr(svar), None, None, _ptr(mu), _ptr(var), n_cand, n_cand, m, pm,
+                                      pv, pb, _stream()))
+    std_mu_objectives[:, :] = smu.cpu().numpy()
+    std_variance_objectives[:, :] = svar.cpu().numpy()

@@ -157,8 +157,8 @@ int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const doub
 
 /* ------------------------------------------------ opt-in: exact hypervolume improvement
  * hvi[i] = HV(front U {u_i}) - HV(front), u_i = (ucb[0][i], .., ucb[m-1][i]), m = 2 or 3.
- * `front_dev` is (n_front, m) row-major, already non-dominated, clipped to >= ref and
- * sorted by objective 0 ascending (m=2) / objective 2 descending (m=3).  No reference
+ * `front_dev` is (n_front <= 1024, m) row-major, sorted by objective 0 DESCENDING (points
+ * below `ref` are clipped to it; dominated points are harmless).  No reference
  * counterpart (the reference's "HVI" is sum-UCB, acquisition.py:104-108).           */
 int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n_cand, int m,
                const double* front_dev, int n_front, const double* ref_host, void* stream);
