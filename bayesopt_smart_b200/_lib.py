@@ -69,6 +69,9 @@ _SIGNATURES = {
                                       c_longlong, _dp, c_double, c_int, c_longlong, c_int, c_void_p, c_size_t,
                                       c_void_p]),
     "bo_dgemm_nt_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "bo_launch_count": (c_longlong, [c_int]),
+    "bo_profile_enable": (c_int, [c_int]),
+    "bo_profile_read": (c_int, [_dp, POINTER(c_longlong), _dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

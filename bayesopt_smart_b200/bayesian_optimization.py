@@ -20,7 +20,7 @@ from .config import (
     DEFAULT_PRIOR_VARIANCE,
     NUMBA_FLOAT_TYPE,
 )
-from .engine import DeviceGP, require_cuda, to_device
+from .engine import DeviceGP, PinnedMirror, require_cuda, to_device
 from .numba_kernels import (
     compute_prior_mean,
     compute_prior_variance,
@@ -77,6 +77,7 @@ def optimize(
     out = {k: torch.empty((n_cand,) if k == "acq" else (m, n_cand), dtype=torch.float64, device=dev) for k in keys}
     host = dict(mu=mu_objectives, var=variance_objectives, std_mu=std_mu_objectives, std_var=std_variance_objectives,
                 ucb=ucb, acq=acquisition_values)
+    mirror = PinnedMirror()
     last_eval = 0
     iterations = list(range(n_evaluations, total_samples, batch_size))
     for current_eval in iterations:
@@ -106,8 +107,12 @@ def optimize(
         x_next = np.array([input_space[i] for i in idx])
         is_last = current_eval == iterations[-1]
         if callbacks or is_last:
+            staged = {k: mirror.get(k, tuple(out[k].shape)) for k in keys}
             for k in keys:
-                host[k][...] = out[k].cpu().numpy()
+                staged[k].copy_(out[k], non_blocking=True)
+            torch.cuda.synchronize()
+            for k in keys:
+                host[k][...] = staged[k].numpy()
         t3 = time.perf_counter()
 
         for b_idx, point in enumerate(x_next):

@@ -1,6 +1,10 @@
 // api.cu -- the exported C ABI (include/bo_b200.h).  Argument checking, workspace carving, error state.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "dense.cuh"
 #include "factor.cuh"
 #include "gemm.cuh"
@@ -22,6 +26,48 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return BO_ERR_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfState {
+  std::mutex mu;
+  bool on = false;
+  std::vector<cudaEvent_t> pool;                       // reusable events
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> live;  // recorded (start, stop) pairs
+  cudaEvent_t pending = nullptr;
+  double flops = 0.0;
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+ProfState g_prof;
+}  // namespace
+
+bool profile_enabled() { return g_prof.on; }
+void profile_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!g_prof.on) return;
+  g_prof.pending = g_prof.get();
+  cudaEventRecord(g_prof.pending, st);
+}
+void profile_end(cudaStream_t st, double flops) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!g_prof.on || !g_prof.pending) return;
+  cudaEvent_t stop = g_prof.get();
+  cudaEventRecord(stop, st);
+  g_prof.live.emplace_back(g_prof.pending, stop);
+  g_prof.pending = nullptr;
+  g_prof.flops += flops;
 }
 
 int device_sm_count() {
@@ -134,6 +180,35 @@ int bo_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes
   if (cc_minor) *cc_minor = prop.minor;
   if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
   if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+  return BO_OK;
+}
+
+long long bo_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int bo_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.on = on != 0;
+  return BO_OK;
+}
+
+int bo_profile_read(double* total_ms, long long* launches, double* flops) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  double ms = 0.0;
+  for (auto& pr : g_prof.live) {
+    BO_CUDA(cudaEventSynchronize(pr.second));
+    float t = 0.f;
+    BO_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+    ms += t;
+    g_prof.pool.push_back(pr.first);
+    g_prof.pool.push_back(pr.second);
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (long long)g_prof.live.size();
+  if (flops) *flops = g_prof.flops;
+  g_prof.live.clear();
+  g_prof.flops = 0.0;
   return BO_OK;
 }
 

@@ -20,6 +20,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 #define BO_LAUNCH_CHECK(name)                                    \
   do {                                                           \
+    ::bo::count_launch();                                        \
     cudaError_t _e = cudaGetLastError();                         \
     if (_e != cudaSuccess) return ::bo::cuda_fail(_e, name);     \
   } while (0)
@@ -45,6 +46,11 @@ struct ObjParams {
 };
 
 int device_sm_count();
+void count_launch();
+// live CUDA-event timing of the dominant kernel (see bo_profile_enable in bo_b200.h)
+bool profile_enabled();
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st, double flops);
 
 // ---------------------------------------------------------------- geometry of the packed operands
 // W (= L^-1, lower triangular, npad x npad) and K* (npad x candidates) are stored as 16 KB tiles in

@@ -384,8 +384,15 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     if (rc) return rc;
     // grid: candidate tile fastest so that concurrently resident CTAs stream the same W tiles (L2 hits)
     const unsigned grid = (unsigned)(m * npairs) * (unsigned)tiles;
+    const bool prof = profile_enabled();
+    if (prof) profile_begin(stream);
     trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp, p.nb,
                                                              p.chunk_tiles, tiles);
+    // algorithmic work of this launch: m * N^2 flops per live candidate
+    if (prof) {
+      const long long live = (remaining < p.ld_chunk ? remaining : p.ld_chunk);
+      profile_end(stream, (double)live * m * (double)n * (double)n);
+    }
     BO_LAUNCH_CHECK("trmm_sumsq_kernel");
     const int chunk_cands = tiles * TN;
     finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(

@@ -221,3 +221,71 @@ def device_info() -> dict:
     _lib.check(lib.bo_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr), ctypes.byref(l2),
                                   ctypes.byref(hbm)))
     return dict(sm_count=sm.value, cc=(maj.value, mnr.value), l2_bytes=l2.value, hbm_bytes=hbm.value)
+
+
+class PinnedMirror:
+    """Grow-only pinned host tensors keyed by name: D2H targets that do not reallocate per iteration."""
+
+    def __init__(self):
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, key: str, shape, dtype=_F64) -> torch.Tensor:
+        buf = self._bufs.get(key)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self._bufs[key] = buf
+        return buf
+
+
+def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean, prior_variance, length_scales,
+                       betas, current_eval: int, batch_size: int, *, mirror: Optional[PinnedMirror] = None,
+                       index_base: int = 0, want_host=("mu", "var", "acq")) -> dict:
+    """Steps b..h of the reference loop (bayesian_optimization.py:129-207) with HOST buffers in and out.
+
+    Host -> device: x_vector[:n], y_vector[:n], input_space.  Device -> host: the arrays the reference's
+    ``state`` dict exposes (mu_objectives, variance_objectives, acquisition_values) plus the selected batch.
+    Returns host NumPy views (pinned) under "mu", "var", "acq", the batch rows "x_next", their global
+    indices "idx", and the device-side candidate lists used for a multi-GPU merge.
+    """
+    mirror = mirror or PinnedMirror()
+    dev = gp.device
+    n = int(current_eval)
+    x_dev = to_device(x_vector[:n], _F64, dev)
+    y_dev = to_device(y_vector[:n], _F64, dev)
+    cand_dev = to_device(input_space, None, dev)
+    gp.fit(x_dev, y_dev, prior_mean, prior_variance, length_scales, n)
+    n_cand = cand_dev.shape[0]
+    cache = getattr(gp, "_iter_out", None)
+    if cache is None or cache["acq"].numel() != n_cand or cache["mu"].shape[0] != gp.m:
+        cache = {k: torch.empty((n_cand,) if k == "acq" else (gp.m, n_cand), dtype=_F64, device=dev)
+                 for k in ("mu", "var", "std_mu", "std_var", "ucb", "acq")}
+        gp._iter_out = cache
+    gp.score(cand_dev, betas, out=cache)
+    k = min(n_cand, batch_size + 16)
+    vals, idx = gp.topk(cache["acq"], k, index_base)
+    flags = gp.match_rows(idx, cand_dev, x_dev, index_base)
+    res = {"top_vals_dev": torch.where(flags.bool(), torch.full_like(vals, float("-inf")), vals),
+           "top_idx_dev": idx, "device": cache}
+    hv = mirror.get("top_vals", (k,))
+    hi = mirror.get("top_idx", (k,), torch.int64)
+    hf = mirror.get("top_flags", (k,), torch.uint8)
+    hv.copy_(vals, non_blocking=True)
+    hi.copy_(idx, non_blocking=True)
+    hf.copy_(flags, non_blocking=True)
+    for key in want_host:
+        h = mirror.get(key, tuple(cache[key].shape))
+        h.copy_(cache[key], non_blocking=True)
+        res[key] = h.numpy()
+    torch.cuda.synchronize(dev)
+    keep = (hf.numpy() == 0) & (hi.numpy() >= 0)
+    if keep.sum() < batch_size and k < n_cand:  # rare: the slack was eaten by already-evaluated rows
+        _, sel = gp.select(cand_dev, cache["acq"], x_dev, batch_size, index_base)
+    else:
+        sel = hi.numpy()[keep][:batch_size]
+    res["idx"] = np.array(sel, dtype=np.int64)
+    local = res["idx"] - index_base
+    if isinstance(input_space, torch.Tensor):
+        res["x_next"] = input_space[torch.from_numpy(local)].cpu().numpy() if len(local) else np.array([])
+    else:
+        res["x_next"] = np.array([input_space[i] for i in local])
+    return res

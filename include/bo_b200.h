@@ -188,6 +188,17 @@ int bo_variance_dense_f64(double* var_dev, long long ld_var, const double* kstar
  * used by bench.py / tests to report the kernel's throughput next to the roofline.   */
 int bo_dgemm_nt_f64(double* C_dev, const double* A_dev, const double* B_dev, int n, void* stream);
 
+/* Kernel launches issued by this library since the last reset (process-wide counter; bench.py's
+ * "gpu_launches").  reset != 0 zeroes it after reading.                                           */
+long long bo_launch_count(int reset);
+
+/* Live timing of the dominant kernel (trmm_sumsq_kernel) with CUDA events recorded on the launching
+ * stream inside bo_score_f64.  bo_profile_enable(1) starts collecting, bo_profile_read() synchronises
+ * the recorded events and returns the summed duration (ms), launch count and algorithmic FLOPs
+ * (m * N^2 per candidate) since the last read, then clears them.                      */
+int bo_profile_enable(int on);
+int bo_profile_read(double* total_ms, long long* launches, double* flops);
+
 #ifdef __cplusplus
 }
 #endif

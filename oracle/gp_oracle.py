@@ -29,6 +29,8 @@ Parity status
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # Constants: reference bayesopt/config.py:54-66 (float64 build).
@@ -42,19 +44,49 @@ MIN_VARIANCE = 1e-10
 # ----------------------------------------------------------------------------
 
 
+_POOL = None
+_TILE = 512
+
+
+def _pool():
+    """Host thread pool: NumPy ufuncs release the GIL, so column tiles run on all cores (the reference
+    runs these loops under Numba ``prange``, numba_kernels.py:352, :432)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+    return _POOL
+
+
+def _sq_tile(a: np.ndarray, bt: np.ndarray, out: np.ndarray) -> None:
+    """out[i, j] = sum_k (a[i,k] - bt[k,j])^2, accumulated k = 0..d-1 (direct difference form)."""
+    tmp = np.empty_like(out)
+    for k in range(a.shape[1]):
+        np.subtract(a[:, k][:, None], bt[k][None, :], out=tmp)
+        np.multiply(tmp, tmp, out=tmp)
+        if k == 0:
+            out[...] = tmp
+        else:
+            out += tmp
+
+
 def _sq_dists(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """Direct-difference squared distances, (len(a), len(b)).
 
     Reference: ``diff = x[i] - x[j]; sq = dot(diff, diff)``
-    (numba_kernels.py:354-355 and :436-437).  Accumulated dimension by dimension
-    so the memory footprint stays (na, nb) and the summation order is k=0..d-1.
+    (numba_kernels.py:354-355 and :436-437).  Cache-blocked over column tiles on the host thread pool;
+    the summation order is k = 0..d-1 for every pair.
     """
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float64)
-    for k in range(a.shape[1]):
-        diff = a[:, k][:, None] - b[:, k][None, :]
-        out += diff * diff
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    bt = np.ascontiguousarray(np.asarray(b, dtype=np.float64).T)
+    out = np.empty((a.shape[0], bt.shape[1]), dtype=np.float64)
+    tiles = [(j, min(j + _TILE, bt.shape[1])) for j in range(0, bt.shape[1], _TILE)]
+    if len(tiles) <= 1:
+        for j0, j1 in tiles:
+            _sq_tile(a, bt[:, j0:j1], out[:, j0:j1])
+        return out
+    list(_pool().map(lambda t: _sq_tile(a, bt[:, t[0]:t[1]], out[:, t[0]:t[1]]), tiles))
     return out
 
 
@@ -90,11 +122,29 @@ def ref_invert_k(current_eval, kernel_matrix):
 
 
 def ref_update_k_star(k_star, x_vector, input_space, last_eval, current_eval, prior_variance, length_scales):
-    """Cross kernel, in place.  Reference numba_kernels.py:406-442."""
+    """Cross kernel, in place.  Reference numba_kernels.py:406-442 (one squared distance per pair, one exp
+    per objective: :436-442)."""
     n_obj = k_star.shape[0]
-    sq = _sq_dists(x_vector[last_eval:current_eval], input_space)
-    for o in range(n_obj):
-        k_star[o, last_eval:current_eval, :] = prior_variance[o] * np.exp(-0.5 * sq / (length_scales[o] ** 2))
+    a = np.ascontiguousarray(x_vector[last_eval:current_eval], dtype=np.float64)
+    bt = np.ascontiguousarray(np.asarray(input_space, dtype=np.float64).T)
+    coef = [-0.5 / (length_scales[o] ** 2) for o in range(n_obj)]
+
+    def work(t):
+        j0, j1 = t
+        sq = np.empty((a.shape[0], j1 - j0))
+        _sq_tile(a, bt[:, j0:j1], sq)
+        for o in range(n_obj):
+            dst = k_star[o, last_eval:current_eval, j0:j1]
+            np.multiply(sq, coef[o], out=dst)
+            np.exp(dst, out=dst)
+            dst *= prior_variance[o]
+
+    tiles = [(j, min(j + _TILE, bt.shape[1])) for j in range(0, bt.shape[1], _TILE)]
+    if len(tiles) <= 1:
+        for t in tiles:
+            work(t)
+    else:
+        list(_pool().map(work, tiles))
 
 
 def ref_update_mean(mu_objectives, k_star, inverted_kernel_matrix, y_vector, prior_mean, current_eval):
@@ -104,7 +154,8 @@ def ref_update_mean(mu_objectives, k_star, inverted_kernel_matrix, y_vector, pri
         kinv = np.ascontiguousarray(inverted_kernel_matrix[o, :n, :n])
         delta = np.ascontiguousarray(y_vector[:n, o] - prior_mean[o])  # :477-479
         partial = kinv @ delta  # :483
-        mu_objectives[o, :] = prior_mean[o] + np.ascontiguousarray(k_star[o, :n, :].T) @ partial  # :486-488
+        # :486-488 (the reference first makes a contiguous copy of k_star.T; the product is the same gemv)
+        mu_objectives[o, :] = prior_mean[o] + k_star[o, :n, :].T @ partial
 
 
 def ref_update_variance(variance_objectives, k_star, inverted_kernel_matrix, prior_variance, current_eval):
