@@ -21,18 +21,19 @@ namespace {
 // ------------------------------------------------------------------------------------------- K* tiles
 // B tile (kt, c): 16 k x 128 candidates -> [wn(4)][j(4)][sp(2)][lane(32)][q(2)]
 //   element = K*[kt*16 + (sp*2+q)*4 + t][c*128 + wn*32 + j*8 + g],  lane = g*4 + t
-// Warp w of the CTA owns columns wn = w>>1, j in {2*(w&1), 2*(w&1)+1} for ALL k, so the mean dot product
-// needs no cross-warp reduction.
+// A CTA (4 warps, <= 128 registers so that it can co-reside with the 1-CTA/SM TRMM kernel) produces half a
+// tile: warp w owns columns wn = 2*half + (w>>1), j in {2*(w&1), 2*(w&1)+1} for ALL k, so the mean dot
+// product needs no cross-warp reduction.
 template <typename CT, int DMAX, int MOBJ>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 4)
     kstar_pack_kernel(double* __restrict__ Kp, double* __restrict__ meandot, const CT* __restrict__ cand, int ldc,
                       long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk,
                       const double* __restrict__ x, int ldx, int n, int npad, int d, const double* __restrict__ alpha,
                       ObjParams hp) {
-  const int c = blockIdx.x;
+  const int c = blockIdx.x >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wn = warp >> 1, j0 = (warp & 1) * 2;
+  const int wn = (blockIdx.x & 1) * 2 + (warp >> 1), j0 = (warp & 1) * 2;
   const int nkt = npad / TK;
 
   double cc[2][DMAX];
@@ -179,8 +180,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
   for (int rb = 0; rb < n_rb; ++rb) {
     const int ib = rb == 0 ? ib_first : pr;
     const int nkt = (ib + 1) * KT_PER_BLOCK;
-    // k-tiles at or beyond this one only meet zeros of the lower-triangular W in this warp's 64 rows
-    const int kt_skip = (ib * TM + wm * 64 + 64) / TK;
+    // Inside the diagonal 128x128 block W is lower triangular: for this warp's rows (wm*64 + 8i + g) the
+    // k-tile kd (16 wide, counted from the start of the diagonal block) only meets non-zeros for row
+    // atoms i >= 2*(kd - 4*wm); tiles with kd - 4*wm >= 4 are skipped entirely.
+    const int kt_diag = ib * KT_PER_BLOCK;
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -189,24 +192,40 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
 
     for (int kt = 0; kt < nkt; ++kt) {
       mbar_wait(&full[stage], phase);
-      if (kt < kt_skip) {
-        const double* a_base = sA + stage * TILE_DOUBLES + wm * 1024 + lane * 2;
-        const double* b_base = sB + stage * TILE_DOUBLES + wn * 512 + lane * 2;
+      const double* a_base = sA + stage * TILE_DOUBLES + wm * 1024 + lane * 2;
+      const double* b_base = sB + stage * TILE_DOUBLES + wn * 512 + lane * 2;
+      const int i_min = 2 * (kt - kt_diag - 4 * wm);  // <= 0: every row atom is live
+      if (i_min <= 0) {
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-          double2 a[8], b[4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = lds128(a_base + (i * 2 + sp) * 64);
+          double2 b[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 8; ++i) {
+            const double2 a = lds128(a_base + (i * 2 + sp) * 64);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
+          }
+        }
+      } else if (i_min < 8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+        for (int sp = 0; sp < 2; ++sp) {
+          double2 b[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
+#pragma unroll
+          for (int i = 2; i < 8; ++i) {
+            if (i >= i_min) {  // warp-uniform
+              const double2 a = lds128(a_base + (i * 2 + sp) * 64);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
+            }
+          }
         }
       }
       __syncwarp();
@@ -294,7 +313,7 @@ int launch_kstar_m(int m, dim3 grid, cudaStream_t st, double* Kp, double* meando
                    long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x, int ldx,
                    int n, int npad, int d, const double* alpha, const ObjParams& hp) {
 #define BO_KS(MO)                                                                                              \
-  kstar_pack_kernel<CT, DMAX, MO><<<grid, 256, 0, st>>>(Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles,    \
+  kstar_pack_kernel<CT, DMAX, MO><<<grid, 128, 0, st>>>(Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles,    \
                                                         ld_chunk, x, ldx, n, npad, d, alpha, hp)
   switch (m) {
     case 1: BO_KS(1); break;
@@ -324,21 +343,57 @@ int launch_kstar(int m, int d, dim3 grid, cudaStream_t st, double* Kp, double* m
 }  // namespace
 
 // =========================================================================================== host driver
+namespace {
+
+// Helper stream (lowest priority) + events used to generate K* for chunk i+1 while TRMM(i) runs on the
+// caller's stream.  One set per device, created lazily; purely an execution resource (no data state).
+struct Overlap {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t inputs_ready = nullptr;
+  cudaEvent_t kstar_done[2] = {nullptr, nullptr};
+  cudaEvent_t buffer_free[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+
+Overlap* overlap_for_current_device() {
+  static Overlap table[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  Overlap& o = table[dev];
+  if (!o.ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent
+    if (cudaStreamCreateWithPriority(&o.aux, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    bool good = cudaEventCreateWithFlags(&o.inputs_ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; b < 2; ++b) {
+      good = good && cudaEventCreateWithFlags(&o.kstar_done[b], cudaEventDisableTiming) == cudaSuccess;
+      good = good && cudaEventCreateWithFlags(&o.buffer_free[b], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!good) return nullptr;
+    o.ok = true;
+  }
+  return &o;
+}
+
+}  // namespace
+
 ScorePlan make_score_plan(int n, int m, long long n_cand) {
   ScorePlan p;
   p.npad = round_up(n, TM);
   p.nb = p.npad / TM;
   const long long tiles = (n_cand + TN - 1) / TN;
-  // two CTAs' worth of tiles per SM per (objective, row pair): every wave of the TRMM grid is full
-  long long ct = 2LL * device_sm_count();
-  // cap the K* staging buffer near 3 GB
+  // four CTAs' worth of tiles per SM per (objective, row pair): every TRMM wave is full and the launch
+  // tail is amortised over 32 waves
+  long long ct = 4LL * device_sm_count();
+  // cap each of the two K* staging buffers near 1.5 GB
   const long long bytes_per_tile = (long long)m * p.npad * TN * sizeof(double);
-  const long long cap = (3LL << 30) / bytes_per_tile;
+  const long long cap = (3LL << 29) / bytes_per_tile;
   if (ct > cap) ct = cap < 1 ? 1 : cap;
   if (ct > tiles) ct = tiles;
   if (ct < 1) ct = 1;
   p.chunk_tiles = (int)ct;
   p.ld_chunk = ct * TN;
+  p.nbuf = (tiles > ct) ? 2 : 1;  // double buffering only pays when there is more than one chunk
   p.kp_doubles = (size_t)m * ct * p.npad * TN;
   p.part_doubles = (size_t)m * p.nb * p.ld_chunk;
   p.mean_doubles = (size_t)m * p.ld_chunk;
@@ -346,7 +401,7 @@ ScorePlan make_score_plan(int n, int m, long long n_cand) {
 }
 
 size_t score_workspace_bytes(const ScorePlan& p) {
-  return align256(p.kp_doubles * 8) + align256(p.part_doubles * 8) + align256(p.mean_doubles * 8);
+  return p.nbuf * (align256(p.kp_doubles * 8) + align256(p.mean_doubles * 8)) + align256(p.part_doubles * 8);
 }
 
 int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, int ldc, long long n_cand,
@@ -365,28 +420,68 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     attr_set = true;
   }
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  double* Kp = reinterpret_cast<double*>(ws);
-  double* part = reinterpret_cast<double*>(ws + align256(p.kp_doubles * 8));
-  double* meandot = reinterpret_cast<double*>(ws + align256(p.kp_doubles * 8) + align256(p.part_doubles * 8));
+  double* Kp[2];
+  double* meandot[2];
+  size_t off = 0;
+  for (int b = 0; b < p.nbuf; ++b) {
+    Kp[b] = reinterpret_cast<double*>(ws + off);
+    off += align256(p.kp_doubles * 8);
+    meandot[b] = reinterpret_cast<double*>(ws + off);
+    off += align256(p.mean_doubles * 8);
+  }
+  double* part = reinterpret_cast<double*>(ws + off);
   const long long strideWp = (long long)wpack_tile_offset(p.nb) * TILE_DOUBLES;
   const int npairs = (p.nb + 1) / 2;
+  const long long n_chunks = (n_cand + p.ld_chunk - 1) / p.ld_chunk;
 
-  for (long long cand0 = 0; cand0 < n_cand; cand0 += p.ld_chunk) {
+  Overlap* ov = (p.nbuf == 2) ? overlap_for_current_device() : nullptr;
+  cudaStream_t ks_stream = ov ? ov->aux : stream;
+  if (ov) {
+    BO_CUDA(cudaEventRecord(ov->inputs_ready, stream));  // factor / candidates produced on the caller's stream
+    BO_CUDA(cudaStreamWaitEvent(ov->aux, ov->inputs_ready, 0));
+  }
+
+  auto chunk_tiles_of = [&](long long ci) {
+    const long long cand0 = ci * p.ld_chunk;
     const long long remaining = n_cand - cand0;
-    const int tiles = (int)((remaining < p.ld_chunk ? remaining : p.ld_chunk) + TN - 1) / TN;
+    return (int)(((remaining < p.ld_chunk ? remaining : p.ld_chunk) + TN - 1) / TN);
+  };
+  auto launch_kstar_chunk = [&](long long ci) -> int {
+    const int b = (int)(ci % p.nbuf);
+    const long long cand0 = ci * p.ld_chunk;
+    const int tiles = chunk_tiles_of(ci);
+    if (ov && ci >= 2) BO_CUDA(cudaStreamWaitEvent(ov->aux, ov->buffer_free[b], 0));  // TRMM(ci-2) has drained it
     int rc;
     if (cand_kind == BO_CAND_I64)
-      rc = launch_kstar<long long>(m, d, dim3(tiles), stream, Kp, meandot, static_cast<const long long*>(cand), ldc,
-                                   cand0, n_cand, p.chunk_tiles, p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
+      rc = launch_kstar<long long>(m, d, dim3(2 * tiles), ks_stream, Kp[b], meandot[b],
+                                   static_cast<const long long*>(cand), ldc, cand0, n_cand, p.chunk_tiles,
+                                   p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
     else
-      rc = launch_kstar<double>(m, d, dim3(tiles), stream, Kp, meandot, static_cast<const double*>(cand), ldc, cand0,
-                                n_cand, p.chunk_tiles, p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
+      rc = launch_kstar<double>(m, d, dim3(2 * tiles), ks_stream, Kp[b], meandot[b], static_cast<const double*>(cand),
+                                ldc, cand0, n_cand, p.chunk_tiles, p.ld_chunk, x, ldx, n, p.npad, alpha, hp);
     if (rc) return rc;
+    if (ov) BO_CUDA(cudaEventRecord(ov->kstar_done[b], ov->aux));
+    return BO_OK;
+  };
+
+  // software pipeline: K*(0); for each chunk: K*(i+1) on the helper stream, then TRMM(i) + finalize(i)
+  int rc = launch_kstar_chunk(0);
+  if (rc) return rc;
+  for (long long ci = 0; ci < n_chunks; ++ci) {
+    const int b = (int)(ci % p.nbuf);
+    const long long cand0 = ci * p.ld_chunk;
+    const long long remaining = n_cand - cand0;
+    const int tiles = chunk_tiles_of(ci);
+    if (ov && ci + 1 < n_chunks) {
+      rc = launch_kstar_chunk(ci + 1);
+      if (rc) return rc;
+    }
+    if (ov) BO_CUDA(cudaStreamWaitEvent(stream, ov->kstar_done[b], 0));
     // grid: candidate tile fastest so that concurrently resident CTAs stream the same W tiles (L2 hits)
     const unsigned grid = (unsigned)(m * npairs) * (unsigned)tiles;
     const bool prof = profile_enabled();
     if (prof) profile_begin(stream);
-    trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp, p.nb,
+    trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp[b], p.nb,
                                                              p.chunk_tiles, tiles);
     // algorithmic work of this launch: m * N^2 flops per live candidate
     if (prof) {
@@ -394,11 +489,16 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
       profile_end(stream, (double)live * m * (double)n * (double)n);
     }
     BO_LAUNCH_CHECK("trmm_sumsq_kernel");
+    if (ov) BO_CUDA(cudaEventRecord(ov->buffer_free[b], stream));
     const int chunk_cands = tiles * TN;
     finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(
-        out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld, cand0, n_cand, part, meandot, p.ld_chunk,
-        chunk_cands, p.nb, m, hp, min_variance);
+        out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld, cand0, n_cand, part, meandot[b],
+        p.ld_chunk, chunk_cands, p.nb, m, hp, min_variance);
     BO_LAUNCH_CHECK("finalize_kernel");
+    if (!ov && ci + 1 < n_chunks) {
+      rc = launch_kstar_chunk(ci + 1);
+      if (rc) return rc;
+    }
   }
   return BO_OK;
 }

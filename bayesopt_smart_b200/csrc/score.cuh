@@ -8,6 +8,7 @@ struct ScorePlan {
   int npad = 0, nb = 0;
   int chunk_tiles = 0;      // candidate tiles (of 128) per chunk
   long long ld_chunk = 0;   // chunk_tiles * 128
+  int nbuf = 1;             // K* staging buffers (2 = generate chunk i+1 while TRMM(i) runs)
   size_t kp_doubles = 0, part_doubles = 0, mean_doubles = 0;
 };
 ScorePlan make_score_plan(int n, int m, long long n_cand);
