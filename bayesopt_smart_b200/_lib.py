@@ -35,6 +35,7 @@ _SIGNATURES = {
     "bo_inverse_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bo_inverse_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
     "bo_npad": (c_int, [c_int]),
+    "bo_last_clamped_pivots": (c_int, []),
     "bo_wpack_doubles": (c_size_t, [c_int]),
     "bo_fit_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bo_gp_fit_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _dp, _dp,

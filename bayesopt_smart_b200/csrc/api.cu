@@ -117,9 +117,11 @@ __global__ void pad_copy_kernel(double* __restrict__ A, int npad, const double* 
 }
 
 struct FitBuffers {
-  double *A, *W, *T, *D, *scratch;
+  double *A, *W, *T, *D, *scratch, *pol;
   int* info;
 };
+
+thread_local int g_last_clamped = 0;
 
 size_t carve_fit(FitBuffers* fb, void* ws, int npad, int m) {
   unsigned char* p = static_cast<unsigned char*>(ws);
@@ -136,21 +138,25 @@ size_t carve_fit(FitBuffers* fb, void* ws, int npad, int m) {
   if (fb) fb->scratch = reinterpret_cast<double*>(p + off);
   off += align256(alpha_scratch_doubles(npad, m) * sizeof(double));
   if (fb) fb->info = reinterpret_cast<int*>(p + off);
-  off += align256((size_t)m * sizeof(int));
+  off += align256((size_t)2 * m * sizeof(int));
+  if (fb) fb->pol = reinterpret_cast<double*>(p + off);
+  off += align256((size_t)2 * m * sizeof(double));
   return off;
 }
 
 // factor the m padded matrices in fb.A, leave W = L^-1 in fb.W; synchronises to read the pivot status
-int factor_and_invert(const FitBuffers& fb, int npad, int m, cudaStream_t st) {
+int factor_and_invert(const FitBuffers& fb, int npad, int m, double jitter, cudaStream_t st) {
   const long long strideA = (long long)npad * npad, strideD = (long long)npad * 64;
-  BO_CUDA(cudaMemsetAsync(fb.info, 0, sizeof(int) * m, st));
-  int rc = cholesky_blocked(fb.A, npad, strideA, npad, m, fb.D, strideD, fb.info, st);
+  BO_CUDA(cudaMemsetAsync(fb.info, 0, sizeof(int) * 2 * m, st));
+  int rc = cholesky_blocked(fb.A, npad, strideA, npad, m, fb.D, strideD, fb.info, fb.pol, nullptr, jitter, 1, st);
   if (rc) return rc;
   rc = tri_inverse(fb.W, npad, strideA, fb.A, npad, strideA, fb.D, strideD, fb.T, strideA / 2, npad, m, st);
   if (rc) return rc;
-  int info_h[BO_MAX_OBJECTIVES] = {0, 0, 0, 0};
-  BO_CUDA(cudaMemcpyAsync(info_h, fb.info, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  int info_h[2 * BO_MAX_OBJECTIVES] = {0, 0, 0, 0, 0, 0, 0, 0};
+  BO_CUDA(cudaMemcpyAsync(info_h, fb.info, sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, st));
   BO_CUDA(cudaStreamSynchronize(st));
+  g_last_clamped = 0;
+  for (int o = 0; o < m; ++o) g_last_clamped += info_h[m + o];
   for (int o = 0; o < m; ++o) {
     if (info_h[o] != 0) {
       set_error("Matrix is not positive definite (objective %d, pivot %d)", o, info_h[o]);
@@ -212,6 +218,8 @@ int bo_profile_read(double* total_ms, long long* launches, double* flops) {
   return BO_OK;
 }
 
+int bo_last_clamped_pivots(void) { return g_last_clamped; }
+
 int bo_npad(int n) { return round_up(n, TM); }
 size_t bo_wpack_doubles(int n) { return (size_t)wpack_tile_offset(round_up(n, TM) / TM) * TILE_DOUBLES; }
 
@@ -243,7 +251,7 @@ int bo_inverse_f64(double* Kinv_dev, const double* K_dev, int ldk, int n, int m,
   carve_fit(&fb, workspace_dev, npad, m);
   pad_copy_kernel<<<dim3((npad + 127) / 128, npad, m), 128, 0, st>>>(fb.A, npad, K_dev, ldk, n, jitter);
   BO_LAUNCH_CHECK("pad_copy_kernel");
-  int rc = factor_and_invert(fb, npad, m, st);
+  int rc = factor_and_invert(fb, npad, m, jitter, st);
   if (rc) return rc;
   GemmArgs g;  // Kinv = W^T W   (C[i][j] = sum_k W[k][i] W[k][j])
   g.M = n; g.N = n; g.K = npad;
@@ -280,7 +288,7 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
   const long long strideA = (long long)npad * npad;
   rc = gram(fb.A, npad, strideA, x_dev, ldx, 0, n, npad, d, m, hp, jitter, st);
   if (rc) return rc;
-  rc = factor_and_invert(fb, npad, m, st);
+  rc = factor_and_invert(fb, npad, m, jitter, st);
   if (rc) return rc;
   rc = compute_alpha(alpha_dev, fb.W, npad, strideA, y_dev, ldy, n, npad, m, hp, fb.scratch, st);
   if (rc) return rc;

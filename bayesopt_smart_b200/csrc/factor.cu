@@ -50,16 +50,23 @@ __global__ void gram_kernel(double* __restrict__ K, long long ldk, long long str
 
 // ----------------------------------------------------------------------------------------- potf2 + inverse
 // One CTA per matrix in the batch.  S = lower Cholesky factor of the 64x64 diagonal block, X = S^-1.
+//
+// Pivot policy (pol[2b] = floor, pol[2b+1] = negative tolerance): in exact arithmetic every pivot of
+// K + jitter*I is >= jitter, so a pivot that rounding pushed below the floor -- but not below -tolerance --
+// is clamped to the floor (counted in info[batch + b]); a pivot below -tolerance or NaN means the input is
+// genuinely indefinite and is reported in info[b] (numpy LinAlgError at the API).
 __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, long long lda, long long strideA,
                                                         double* __restrict__ D, long long strideD,
-                                                        int* __restrict__ info, int j0) {
+                                                        int* __restrict__ info, int j0,
+                                                        const double* __restrict__ pol, int batch) {
   extern __shared__ double sm[];
   double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
   double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
-  __shared__ int bad;
+  __shared__ int bad, nclamp;
   const int tid = threadIdx.x;
+  const double floor_piv = pol[2 * blockIdx.x], neg_tol = pol[2 * blockIdx.x + 1];
   double* Ab = A + (long long)blockIdx.x * strideA + (long long)j0 * lda + j0;
-  if (tid == 0) bad = 0;
+  if (tid == 0) bad = nclamp = 0;
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     S[r][c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
@@ -69,8 +76,14 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
   const int ur = tid >> 2, uc0 = tid & 3;  // trailing update: row ur, columns uc0 + 4q
   for (int j = 0; j < NB; ++j) {
     __syncthreads();  // trailing update of the previous column is complete
-    const double piv = S[j][j];
-    if (tid == 0 && !(piv > 0.0)) bad = (bad == 0) ? (j0 + j + 1) : bad;
+    double piv = S[j][j];
+    if (!(piv >= floor_piv)) {  // also catches NaN
+      if (tid == 0) {
+        if (piv > -neg_tol) ++nclamp;
+        else bad = (bad == 0) ? (j0 + j + 1) : bad;
+      }
+      piv = floor_piv;
+    }
     const double dsq = sqrt(piv);
     __syncthreads();
     if (tid < NB) {
@@ -112,6 +125,64 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
     Db[e] = X[r][c];
   }
   if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, bad);
+  if (tid == 0 && nclamp != 0) atomicAdd(&info[batch + blockIdx.x], nclamp);
+}
+
+// pol[2b] = pivot floor (jitter of the matrix), pol[2b+1] = sqrt(eps) * max diagonal entry
+__global__ void __launch_bounds__(256) chol_policy_kernel(double* __restrict__ pol, const double* __restrict__ A,
+                                                          long long lda, long long strideA, int npad,
+                                                          const double* __restrict__ jit_dev, double jit_scalar,
+                                                          int per_setting) {
+  __shared__ double red[8];
+  const double* Ab = A + (long long)blockIdx.x * strideA;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) mx = fmax(mx, fabs(Ab[(long long)i * (lda + 1)]));
+#pragma unroll
+  for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+    const double jit = jit_dev ? jit_dev[blockIdx.x / per_setting] : jit_scalar;
+    pol[2 * blockIdx.x] = fmax(jit, 2.220446049250313e-16 * mx);  // never a zero floor
+    pol[2 * blockIdx.x + 1] = 1.4901161193847656e-08 * mx;
+  }
+}
+
+// ----------------------------------------------------------------------------------------- panel TRSM
+// P <- P * L_jj^-T by forward substitution (row i of P solves x L_jj^T = p_i), like LAPACK's dtrsm.  An
+// explicit inverse of the diagonal block is NOT used here: it is not backward stable when the block is
+// ill conditioned (cfg1 reaches cond(K) ~ 1e15) and the trailing update then cancels catastrophically.
+// One CTA = 64 rows of the panel; thread r owns row r; L_jj is read from shared memory (broadcast).
+__global__ void __launch_bounds__(64) trsm_panel_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                        int j0, int rows) {
+  extern __shared__ double sm[];
+  double(*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
+  double(*P)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+  double* Ab = A + (long long)blockIdx.y * strideA;
+  const double* Ljj = Ab + (long long)j0 * lda + j0;
+  const int r0 = blockIdx.x * NB;
+  double* Pg = Ab + (long long)(j0 + NB + r0) * lda + j0;
+  const int tid = threadIdx.x;
+  const int live = min(NB, rows - r0);
+  for (int e = tid; e < NB * NB; e += 64) {
+    const int r = e >> 6, c = e & 63;
+    L[r][c] = Ljj[(long long)r * lda + c];
+    P[r][c] = (r < live) ? Pg[(long long)r * lda + c] : 0.0;
+  }
+  __syncthreads();
+  if (tid < live) {
+    for (int c = 0; c < NB; ++c) {
+      double s = P[tid][c];
+      for (int k = 0; k < c; ++k) s = fma(-P[tid][k], L[c][k], s);
+      P[tid][c] = s / L[c][c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 64) {
+    const int r = e >> 6, c = e & 63;
+    if (r < live) Pg[(long long)r * lda + c] = P[r][c];
+  }
 }
 
 // ----------------------------------------------------------------------------------------- small helpers
@@ -208,28 +279,27 @@ int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, 
 }
 
 int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int batch, double* D, long long strideD,
-                     int* info, cudaStream_t stream) {
+                     int* info, double* pol, const double* jit_dev, double jit_scalar, int per_setting,
+                     cudaStream_t stream) {
+  chol_policy_kernel<<<batch, 256, 0, stream>>>(pol, A, lda, strideA, npad, jit_dev, jit_scalar, per_setting);
+  BO_LAUNCH_CHECK("chol_policy_kernel");
   static bool attr_set = false;
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!attr_set) {
     BO_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   for (int j0 = 0; j0 < npad; j0 += NB) {
     double* Dj = D + (long long)(j0 / NB) * NB * NB;
-    potf2_inv_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, Dj, strideD, info, j0);
+    potf2_inv_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, Dj, strideD, info, j0, pol, batch);
     BO_LAUNCH_CHECK("potf2_inv_kernel");
     const int r = npad - j0 - NB;
     if (r <= 0) break;
     double* P = A + (long long)(j0 + NB) * lda + j0;
-    GemmArgs p;  // P <- P * Linv^T   (C[i][c] = sum_k P[i][k] Linv[c][k]); one column tile => in place is safe
-    p.M = r; p.N = NB; p.K = NB;
-    p.A = P; p.lda = lda; p.strideA = strideA;
-    p.B = Dj; p.ldb = NB; p.strideB = strideD;
-    p.C = P; p.ldc = lda; p.strideC = strideA;
-    p.batch = batch;
-    int rc = gemm(p, 0, 0, stream);
-    if (rc) return rc;
+    trsm_panel_kernel<<<dim3((r + NB - 1) / NB, batch), 64, smem, stream>>>(A, lda, strideA, j0, r);
+    BO_LAUNCH_CHECK("trsm_panel_kernel");
+    int rc;
     GemmArgs t;  // trailing -= P P^T (lower tiles only)
     t.M = r; t.N = r; t.K = NB; t.alpha = -1.0; t.beta = 1.0;
     t.A = P; t.lda = lda; t.strideA = strideA;

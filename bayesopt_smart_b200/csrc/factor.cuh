@@ -9,9 +9,13 @@ int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, 
          int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream);
 
 // In-place lower Cholesky of `batch` npad x npad matrices (npad % 64 == 0).  D receives the inverted 64x64
-// diagonal blocks (npad/64 blocks of 4096 doubles per matrix).  info[b] = 1-based failing pivot or 0.
+// diagonal blocks (npad/64 blocks of 4096 doubles per matrix).  info holds 2*batch ints (zeroed by the caller):
+// info[b] = 1-based pivot where the matrix proved indefinite (0 = fine), info[batch+b] = pivots clamped to the
+// floor.  pol: 2*batch doubles of scratch.  The pivot floor of matrix b is jit_dev[b / per_setting] when jit_dev
+// is given, else jit_scalar (see potf2_inv_kernel).
 int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int batch, double* D, long long strideD,
-                     int* info, cudaStream_t stream);
+                     int* info, double* pol, const double* jit_dev, double jit_scalar, int per_setting,
+                     cudaStream_t stream);
 
 // W = L^-1 (lower), T is scratch of npad*npad/2 doubles per matrix.
 int tri_inverse(double* W, long long ldw, long long strideW, const double* L, long long ldl, long long strideL,

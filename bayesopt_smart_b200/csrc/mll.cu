@@ -128,7 +128,9 @@ size_t mll_workspace_bytes(int n, int m, int n_settings) {
   size_t b = 0;
   b += align256((size_t)gs * m * npad * npad * sizeof(double));   // matrices
   b += align256((size_t)gs * m * npad * 64 * sizeof(double));     // inverted diagonal blocks
-  b += align256((size_t)gs * m * sizeof(int));                    // info
+  b += align256((size_t)2 * gs * m * sizeof(int));                // info (failed pivot, clamped count)
+  b += align256((size_t)2 * gs * m * sizeof(double));             // pivot policy
+  b += align256((size_t)n_settings * sizeof(double));             // jitters on the device
   b += align256((size_t)m * npad * sizeof(double));               // standardised targets
   b += align256((size_t)n_settings * m * sizeof(double));         // per-objective values
   return b;
@@ -147,10 +149,13 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
   size_t off = 0;
   double* A = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * npad * sizeof(double));
   double* D = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * 64 * sizeof(double));
-  int* info = reinterpret_cast<int*>(ws + off);       off += align256((size_t)gs * m * sizeof(int));
+  int* info = reinterpret_cast<int*>(ws + off);       off += align256((size_t)2 * gs * m * sizeof(int));
+  double* pol = reinterpret_cast<double*>(ws + off);  off += align256((size_t)2 * gs * m * sizeof(double));
+  double* jit_dev = reinterpret_cast<double*>(ws + off); off += align256((size_t)n_settings * sizeof(double));
   double* yt = reinterpret_cast<double*>(ws + off);   off += align256((size_t)m * npad * sizeof(double));
   double* vals = reinterpret_cast<double*>(ws + off);
 
+  BO_CUDA(cudaMemcpyAsync(jit_dev, jitter, sizeof(double) * n_settings, cudaMemcpyHostToDevice, stream));
   ObjParams hp0;
   memset(&hp0, 0, sizeof(hp0));
   for (int o = 0; o < m; ++o) hp0.prior_mean[o] = prior_mean[o];
@@ -177,8 +182,8 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
                     stream);
       if (rc) return rc;
     }
-    BO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * g * m, stream));
-    int rc = cholesky_blocked(A, npad, strideA, npad, g * m, D, strideD, info, stream);
+    BO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * g * m, stream));
+    int rc = cholesky_blocked(A, npad, strideA, npad, g * m, D, strideD, info, pol, jit_dev + s0, 0.0, m, stream);
     if (rc) return rc;
     mll_solve_kernel<<<g * m, 256, solve_smem, stream>>>(vals + (long long)s0 * m, A, npad, strideA, D, strideD, info,
                                                          yt, n, npad, m);

@@ -139,6 +139,16 @@ def cpu_reference_sample(sample_cands: int, chunk: int = 16384):
     return time.perf_counter() - t0, cand.shape[0]
 
 
+def use_all_host_threads() -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def blas_threads() -> int:
     try:
         from threadpoolctl import threadpool_info
@@ -152,6 +162,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     sample = 32768
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_reference_sample(4096)
@@ -183,6 +194,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from bayesopt_smart_b200 import _lib
+    from bayesopt_smart_b200 import distributed as bd
     from bayesopt_smart_b200.engine import DeviceGP, PinnedMirror, hot_path_iteration, to_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,11 +223,8 @@ def run_gpu_arm(args):
         """All-gather each rank's top-k pairs and merge with the same comparator (identical on every rank)."""
         if world == 1:
             return vals, idx
-        gv = torch.empty(world * vals.numel(), dtype=vals.dtype, device=dev)
-        gi = torch.empty(world * idx.numel(), dtype=idx.dtype, device=dev)
-        dist.all_gather_into_tensor(gv, vals)
-        dist.all_gather_into_tensor(gi, idx)
-        return gp.topk_merge(gv, gi, vals.numel())
+        gv, gi = bd.gather_topk(vals, idx)
+        return bd.merge_topk(gp, gv, gi, vals.numel())
 
     def step_resident():
         """a1..a9 with every input already resident in HBM."""
@@ -321,9 +330,10 @@ def run_gpu_arm(args):
     total_cands = n_cand * world * args.steps
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
     # bounded CPU sample of the same workload (reference port), ~10-20 s
-    if args.profile_mode:
+    if args.profile_mode or world > 1:  # the CPU baseline is reported at N = 1 only
         t_cpu, cnt_cpu = float("nan"), 0
     else:
+        use_all_host_threads()
         t_cpu, cnt_cpu = cpu_reference_sample(131072)
     cpu_val = cnt_cpu / t_cpu if cnt_cpu else None
     line = {
@@ -349,9 +359,9 @@ def run_gpu_arm(args):
                      "algorithmic": "m*N^2 flop per candidate = 2.097e6; per launch x candidates in the chunk",
                      "launches": int(nl.value), "avg_launch_ms": ms.value / max(1, nl.value),
                      "share_of_step": ms.value * 1e-3 / secs},
-        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                         "sample": f"{cnt_cpu} of 10^6 grid candidates, one pass, NumPy/OpenBLAS port of the "
-                                   "reference functions (oracle/gp_oracle.py)"},
+        "cpu_baseline": ({"value": cpu_val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                          "sample": f"{cnt_cpu} of 10^6 grid candidates, one pass, NumPy/OpenBLAS port of the "
+                                    "reference functions (oracle/gp_oracle.py)"} if cnt_cpu else None),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

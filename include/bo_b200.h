@@ -79,10 +79,13 @@ int bo_inverse_f64(double* Kinv_dev, const double* K_dev, int ldk, int n, int m,
  * device:  K = gram(x) + jitter I = L L^T,  W = L^-1 (stored tile-packed in the DMMA
  * fragment order of bo_score_f64),  alpha[o] = K^-1 (y[:,o] - prior_mean[o]).
  *   wpack_dev : m * bo_wpack_doubles(n) doubles     alpha_dev : m * bo_npad(n) doubles
- * Synchronising (reports BO_ERR_NOT_PD).
+ * Synchronising.  Pivot policy: in exact arithmetic every Cholesky pivot of K + jitter*I is >= jitter;
+ * a pivot that rounding pushed below that (but above -sqrt(eps)*max diag) is clamped to `jitter`
+ * (count via bo_last_clamped_pivots()); anything more negative, or NaN, returns BO_ERR_NOT_PD.
  * Replaces update_k + invert_k + the "Kinv @ delta_y" half of update_mean
  * (numba_kernels.py:329-403, :477-483) as called at bayesian_optimization.py:129-142. */
 int bo_npad(int n);
+int bo_last_clamped_pivots(void); /* pivots clamped by the last bo_gp_fit_f64 / bo_inverse_f64 on this thread */
 size_t bo_wpack_doubles(int n);
 size_t bo_fit_workspace_bytes(int n, int m);
 int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int ldx, const double* y_dev, int ldy,

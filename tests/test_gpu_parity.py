@@ -193,6 +193,33 @@ def test_cfg1_teacher_forced_iterations(pkg, golden):
     assert np.array_equal(cand[idx], g["x_next"][0])
 
 
+def test_cfg1_ill_conditioned_iterations_do_not_fail(pkg, golden):
+    """Later cfg1 iterations have cond(K + 1e-6 I) ~ 1e15 (entries ~3.5e7, absolute jitter 1e-6): rounding can
+    push a Cholesky pivot below zero although every exact pivot is >= jitter.  The reference's LU inverse
+    limps on there (its own posterior is off by 1e-2..1e-1); the CUDA path must not raise: pivots
+    within rounding of zero are clamped to the jitter.  Replays all 20 teacher-forced iterations."""
+    from bayesopt_smart_b200 import _lib
+    from bayesopt_smart_b200.engine import DeviceGP, to_device
+
+    g = golden("cfg1_trace")
+    ranges = [np.arange(0, 300), np.arange(0, 300)]
+    cand = to_device(np.stack([a.ravel() for a in np.meshgrid(*ranges, indexing="ij")], axis=-1))
+    gp = DeviceGP()
+    clamped = 0
+    for it, n in enumerate(g["iteration"]):
+        hp = g["hyperparams"][it]
+        gp.fit(g["x_vector"], g["y_vector"], g["prior_mean"], hp[2:], hp[:2], int(n))
+        clamped += _lib.load().bo_last_clamped_pivots()
+        out = gp.score(cand, g["betas"])
+        for o in range(2):
+            var = out["var"][o]
+            assert torch.isfinite(out["mu"][o]).all() and torch.isfinite(var).all()
+            assert var.min().item() >= 1e-10 and var.max().item() <= hp[2 + o] * (1 + 1e-9)
+        _, idx = gp.select(cand, out["acq"], to_device(g["x_vector"][: int(n)]), 3)
+        assert len(idx) == 3
+    assert clamped >= 0
+
+
 # ------------------------------------------------------------------ fused path vs the oracle at larger sizes
 
 
