@@ -292,7 +292,7 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
   if (rc) return rc;
   rc = compute_alpha(alpha_dev, fb.W, npad, strideA, y_dev, ldy, n, npad, m, hp, fb.scratch, st);
   if (rc) return rc;
-  rc = pack_w(wpack_dev, (long long)bo_wpack_doubles(n), fb.W, npad, strideA, npad, m, st);
+  rc = pack_w(wpack_dev, (long long)bo_wpack_doubles(n), fb.W, npad, strideA, npad, n, m, st);
   if (rc) return rc;
   BO_CUDA(cudaStreamSynchronize(st));
   return BO_OK;

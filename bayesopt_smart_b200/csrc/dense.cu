@@ -6,6 +6,7 @@
 // functions one by one keep working.
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "rbf.cuh"
 
 namespace bo {
 
@@ -24,7 +25,7 @@ __global__ void kstar_dense_kernel(double* __restrict__ ks, long long ld_row, lo
     sq = fma(diff, diff, sq);
   }
   for (int o = 0; o < m; ++o)
-    ks[o * ld_obj + (long long)e * ld_row + c] = hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]);
+    ks[o * ld_obj + (long long)e * ld_row + c] = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], kExp2Tab);
 }
 
 // t[o][i] = sum_k Kinv[o][i][k] * (y[k][o] - mu0[o])      (one warp per row)

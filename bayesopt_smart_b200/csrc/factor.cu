@@ -3,13 +3,16 @@
 // identity block in the padding, so every GEMM below runs on whole tiles.
 //
 //   gram_kernel        K = var * exp(-0.5 |xi-xj|^2 / ls^2) (+ diag_add), identity padding
-//   potf2_inv_kernel   64x64 diagonal block: in-shared-memory Cholesky and its triangular inverse
-//   cholesky_blocked   right-looking: potf2 -> panel (GEMM with the inverted block) -> trailing SYRK (DMMA)
+//   potf2_kernel       64x64 diagonal block: in-shared-memory Cholesky, one barrier per column
+//   trsm_panel_kernel  panel <- panel * L_jj^-T by substitution (backward stable, like dtrsm)
+//   block_inverse      inverses of all diagonal blocks in parallel (base of W = L^-1 and of the MLL solve)
+//   cholesky_blocked   right-looking: potf2 -> panel TRSM -> trailing SYRK (DMMA)
 //   tri_inverse        W = L^-1 by recursive doubling: W21 = -W22 (L21 W11), two batched GEMMs per level
 //   alpha kernels      alpha = W^T (W (y - mu0))
 //   pack_w_kernel      W -> 16 KB tiles in DMMA fragment order for trmm.cu
 #include "factor.cuh"
 #include "gemm.cuh"
+#include "rbf.cuh"
 
 namespace bo {
 
@@ -41,27 +44,28 @@ __global__ void gram_kernel(double* __restrict__ K, long long ldk, long long str
     sq = fma(diff, diff, sq);
   }
   for (int o = 0; o < m; ++o) {
-    double v = hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]);
+    double v = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], kExp2Tab);
     if (i == j) v += diag_add;
     K[o * strideK + (long long)i * ldk + j] = v;
     K[o * strideK + (long long)j * ldk + i] = v;
   }
 }
 
-// ----------------------------------------------------------------------------------------- potf2 + inverse
-// One CTA per matrix in the batch.  S = lower Cholesky factor of the 64x64 diagonal block, X = S^-1.
+// ----------------------------------------------------------------------------------------- potf2
+// One CTA per matrix in the batch: lower Cholesky factor of the 64x64 diagonal block in shared memory,
+// ONE barrier per column: the trailing update reads the unscaled column j of S and the pivot, the scaled
+// column goes to a second array (nobody reads column j of S again).
 //
 // Pivot policy (pol[2b] = floor, pol[2b+1] = negative tolerance): in exact arithmetic every pivot of
 // K + jitter*I is >= jitter, so a pivot that rounding pushed below the floor -- but not below -tolerance --
 // is clamped to the floor (counted in info[batch + b]); a pivot below -tolerance or NaN means the input is
 // genuinely indefinite and is reported in info[b] (numpy LinAlgError at the API).
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, long long lda, long long strideA,
-                                                        double* __restrict__ D, long long strideD,
-                                                        int* __restrict__ info, int j0,
-                                                        const double* __restrict__ pol, int batch) {
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                    int* __restrict__ info, int j0, const double* __restrict__ pol,
+                                                    int batch) {
   extern __shared__ double sm[];
   double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-  double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+  double(*Lo)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
   __shared__ int bad, nclamp;
   const int tid = threadIdx.x;
   const double floor_piv = pol[2 * blockIdx.x], neg_tol = pol[2 * blockIdx.x + 1];
@@ -70,9 +74,8 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     S[r][c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
-    X[r][c] = 0.0;
+    Lo[r][c] = 0.0;
   }
-  __syncthreads();
   const int ur = tid >> 2, uc0 = tid & 3;  // trailing update: row ur, columns uc0 + 4q
   for (int j = 0; j < NB; ++j) {
     __syncthreads();  // trailing update of the previous column is complete
@@ -84,15 +87,9 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
       }
       piv = floor_piv;
     }
-    const double dsq = sqrt(piv);
-    __syncthreads();
-    if (tid < NB) {
-      if (tid == j) S[j][j] = dsq;
-      else if (tid > j) S[tid][j] = S[tid][j] / dsq;
-    }
-    __syncthreads();
+    if (tid < NB && tid >= j) Lo[tid][j] = (tid == j) ? sqrt(piv) : S[tid][j] / sqrt(piv);
     if (ur > j) {
-      const double lij = S[ur][j];
+      const double lij = S[ur][j] / piv;  // l_ij * l_kj = s_ij * s_kj / piv
 #pragma unroll 4
       for (int q = 0; q < 16; ++q) {
         const int k = uc0 + 4 * q;
@@ -101,8 +98,33 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
     }
   }
   __syncthreads();
-  // X = S^-1 by forward substitution; 4 threads per column split the dot product over k mod 4.
-  // The i loop is uniform across the warp (columns differ per lane) so the shuffles are convergent.
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Ab[(long long)r * lda + c] = Lo[r][c];  // strict upper part of the block becomes exact zeros
+  }
+  if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, bad);
+  if (tid == 0 && nclamp != 0) atomicAdd(&info[batch + blockIdx.x], nclamp);
+}
+
+// ----------------------------------------------------------------------------------------- block inverses
+// D[jb] = L[jb,jb]^-1 for every 64x64 diagonal block, all blocks in parallel (off the Cholesky critical path).
+// Column c of the inverse by forward substitution, 4 threads per column splitting the dot product; the i
+// loop is uniform across the warp so the shuffles are convergent.
+__global__ void __launch_bounds__(256) block_inverse_kernel(double* __restrict__ D, long long strideD,
+                                                            const double* __restrict__ A, long long lda,
+                                                            long long strideA) {
+  extern __shared__ double sm[];
+  double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
+  double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  const int jb = blockIdx.x;
+  const double* Ab = A + (long long)blockIdx.y * strideA + (long long)jb * NB * (lda + 1);
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    S[r][c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
+    X[r][c] = 0.0;
+  }
+  __syncthreads();
   {
     const int c = tid >> 2, q = tid & 3;
     if (q == 0) X[c][c] = 1.0 / S[c][c];
@@ -118,14 +140,8 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
     }
   }
   __syncthreads();
-  double* Db = D + (long long)blockIdx.x * strideD;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    Ab[(long long)r * lda + c] = S[r][c];  // strict upper part of the block becomes exact zeros
-    Db[e] = X[r][c];
-  }
-  if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, bad);
-  if (tid == 0 && nclamp != 0) atomicAdd(&info[batch + blockIdx.x], nclamp);
+  double* Db = D + (long long)blockIdx.y * strideD + (long long)jb * NB * NB;
+  for (int e = tid; e < NB * NB; e += 256) Db[e] = X[e >> 6][e & 63];
 }
 
 // pol[2b] = pivot floor (jitter of the matrix), pol[2b+1] = sqrt(eps) * max diagonal entry
@@ -154,8 +170,8 @@ __global__ void __launch_bounds__(256) chol_policy_kernel(double* __restrict__ p
 // explicit inverse of the diagonal block is NOT used here: it is not backward stable when the block is
 // ill conditioned (cfg1 reaches cond(K) ~ 1e15) and the trailing update then cancels catastrophically.
 // One CTA = 64 rows of the panel; thread r owns row r; L_jj is read from shared memory (broadcast).
-__global__ void __launch_bounds__(64) trsm_panel_kernel(double* __restrict__ A, long long lda, long long strideA,
-                                                        int j0, int rows) {
+__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                         int j0, int rows) {
   extern __shared__ double sm[];
   double(*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
   double(*P)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
@@ -165,21 +181,26 @@ __global__ void __launch_bounds__(64) trsm_panel_kernel(double* __restrict__ A, 
   double* Pg = Ab + (long long)(j0 + NB + r0) * lda + j0;
   const int tid = threadIdx.x;
   const int live = min(NB, rows - r0);
-  for (int e = tid; e < NB * NB; e += 64) {
+  for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     L[r][c] = Ljj[(long long)r * lda + c];
     P[r][c] = (r < live) ? Pg[(long long)r * lda + c] : 0.0;
   }
   __syncthreads();
-  if (tid < live) {
+  {
+    // 4 threads per row split the dot product over k mod 4; the 4 lanes of a row sit in one warp
+    const int r = tid >> 2, q = tid & 3;
     for (int c = 0; c < NB; ++c) {
-      double s = P[tid][c];
-      for (int k = 0; k < c; ++k) s = fma(-P[tid][k], L[c][k], s);
-      P[tid][c] = s / L[c][c];
+      double s = 0.0;
+      for (int k = q; k < c; k += 4) s = fma(P[r][k], L[c][k], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) P[r][c] = (P[r][c] - s) / L[c][c];
+      __syncwarp();
     }
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 64) {
+  for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     if (r < live) Pg[(long long)r * lda + c] = P[r][c];
   }
@@ -237,9 +258,10 @@ __global__ void sum_partials_kernel(double* __restrict__ out, const double* __re
 // ----------------------------------------------------------------------------------------- pack W
 // tile (ib, kt) of W (128 rows x 16 k) -> [wm(2)][i(8)][sp(2)][lane(32)][q(2)]
 //   element = W[ib*128 + wm*64 + i*8 + g][kt*16 + (sp*2+q)*4 + t],  lane = g*4 + t
+// Rows/columns >= n (the identity padding) are written as zeros, so padded K* rows never contribute.
 __global__ void __launch_bounds__(256) pack_w_kernel(double* __restrict__ Wp, long long strideWp,
                                                      const double* __restrict__ W, long long ldw, long long strideW,
-                                                     int nb) {
+                                                     int nb, int n) {
   __shared__ double s[TM][TK + 1];
   const int o = blockIdx.y;
   // decode tile index -> (ib, kt)
@@ -259,7 +281,9 @@ __global__ void __launch_bounds__(256) pack_w_kernel(double* __restrict__ Wp, lo
   for (int e = threadIdx.x; e < TILE_DOUBLES; e += 256) {
     const int q = e & 1, lane = (e >> 1) & 31, sp = (e >> 6) & 1, i = (e >> 7) & 7, wm = e >> 10;
     const int g = lane >> 2, t = lane & 3;
-    dst[e] = s[wm * 64 + i * 8 + g][(sp * 2 + q) * 4 + t];
+    const int lr = wm * 64 + i * 8 + g, lk = (sp * 2 + q) * 4 + t;
+    const bool pad = (ib * TM + lr >= n) || (kt * TK + lk >= n);
+    dst[e] = pad ? 0.0 : s[lr][lk];
   }
   (void)nb;
 }
@@ -286,18 +310,18 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
   static bool attr_set = false;
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BO_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BO_CUDA(cudaFuncSetAttribute(block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     BO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   for (int j0 = 0; j0 < npad; j0 += NB) {
-    double* Dj = D + (long long)(j0 / NB) * NB * NB;
-    potf2_inv_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, Dj, strideD, info, j0, pol, batch);
-    BO_LAUNCH_CHECK("potf2_inv_kernel");
+    potf2_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, info, j0, pol, batch);
+    BO_LAUNCH_CHECK("potf2_kernel");
     const int r = npad - j0 - NB;
     if (r <= 0) break;
     double* P = A + (long long)(j0 + NB) * lda + j0;
-    trsm_panel_kernel<<<dim3((r + NB - 1) / NB, batch), 64, smem, stream>>>(A, lda, strideA, j0, r);
+    trsm_panel_kernel<<<dim3((r + NB - 1) / NB, batch), 256, smem, stream>>>(A, lda, strideA, j0, r);
     BO_LAUNCH_CHECK("trsm_panel_kernel");
     int rc;
     GemmArgs t;  // trailing -= P P^T (lower tiles only)
@@ -309,6 +333,8 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
     rc = gemm(t, 0, 0, stream);
     if (rc) return rc;
   }
+  block_inverse_kernel<<<dim3(npad / NB, batch), 256, smem, stream>>>(D, strideD, A, lda, strideA);
+  BO_LAUNCH_CHECK("block_inverse_kernel");
   return BO_OK;
 }
 
@@ -372,11 +398,11 @@ int compute_alpha(double* alpha, const double* W, long long ldw, long long strid
 }
 size_t alpha_scratch_doubles(int npad, int m) { return (size_t)m * npad * 17; }
 
-int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int m,
+int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int n, int m,
            cudaStream_t stream) {
   const int nb = npad / TM;
   const long long ntiles = wpack_tile_offset(nb);
-  pack_w_kernel<<<dim3((unsigned)ntiles, m), 256, 0, stream>>>(Wp, strideWp, W, ldw, strideW, nb);
+  pack_w_kernel<<<dim3((unsigned)ntiles, m), 256, 0, stream>>>(Wp, strideWp, W, ldw, strideW, nb, n);
   BO_LAUNCH_CHECK("pack_w_kernel");
   return BO_OK;
 }

@@ -12,7 +12,7 @@ int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, 
 // diagonal blocks (npad/64 blocks of 4096 doubles per matrix).  info holds 2*batch ints (zeroed by the caller):
 // info[b] = 1-based pivot where the matrix proved indefinite (0 = fine), info[batch+b] = pivots clamped to the
 // floor.  pol: 2*batch doubles of scratch.  The pivot floor of matrix b is jit_dev[b / per_setting] when jit_dev
-// is given, else jit_scalar (see potf2_inv_kernel).
+// is given, else jit_scalar (see potf2_kernel).
 int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int batch, double* D, long long strideD,
                      int* info, double* pol, const double* jit_dev, double jit_scalar, int per_setting,
                      cudaStream_t stream);
@@ -28,7 +28,7 @@ int compute_alpha(double* alpha, const double* W, long long ldw, long long strid
 size_t alpha_scratch_doubles(int npad, int m);
 
 // W -> fragment-ordered 16 KB tiles (see common.cuh)
-int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int m,
+int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int n, int m,
            cudaStream_t stream);
 
 }  // namespace bo

@@ -14,6 +14,10 @@
 // candidate set is sharded across GPUs (bit-identical top-k for any rank count).
 #include "score.cuh"
 
+#include <stdlib.h>
+
+#include "rbf.cuh"
+
 namespace bo {
 
 namespace {
@@ -21,73 +25,86 @@ namespace {
 // ------------------------------------------------------------------------------------------- K* tiles
 // B tile (kt, c): 16 k x 128 candidates -> [wn(4)][j(4)][sp(2)][lane(32)][q(2)]
 //   element = K*[kt*16 + (sp*2+q)*4 + t][c*128 + wn*32 + j*8 + g],  lane = g*4 + t
-// A CTA (4 warps, <= 128 registers so that it can co-reside with the 1-CTA/SM TRMM kernel) produces half a
-// tile: warp w owns columns wn = 2*half + (w>>1), j in {2*(w&1), 2*(w&1)+1} for ALL k, so the mean dot
-// product needs no cross-warp reduction.
-template <typename CT, int DMAX, int MOBJ>
+// A CTA (4 warps) produces half a tile column: warp w owns columns wn = 2*half + (w>>1),
+// j in {2*(w&1), 2*(w&1)+1} for ALL k, so the mean dot product needs no cross-warp reduction.
+// Training rows (x, alpha) are staged through shared memory in blocks of KS_ROWS rows; D is the padded
+// dimension count (coordinates beyond d are zero on both sides, so the inner loop has no predicates).
+// Rows >= n need no masking: the packed W has zero rows/columns there, and alpha is zero.
+constexpr int KS_ROWS = 256;
+
+template <typename CT, int D, int MOBJ>
 __global__ void __launch_bounds__(128, 4)
     kstar_pack_kernel(double* __restrict__ Kp, double* __restrict__ meandot, const CT* __restrict__ cand, int ldc,
                       long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk,
                       const double* __restrict__ x, int ldx, int n, int npad, int d, const double* __restrict__ alpha,
                       ObjParams hp) {
+  __shared__ double exp_tab[64];
+  __shared__ double xs[KS_ROWS][D + MOBJ];  // row: D coordinates then MOBJ alphas
+  const int tid = threadIdx.x;
+  if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
   const int c = blockIdx.x >> 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int wn = (blockIdx.x & 1) * 2 + (warp >> 1), j0 = (warp & 1) * 2;
   const int nkt = npad / TK;
 
-  double cc[2][DMAX];
+  double cc[2][D];
 #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
     long long ci = cand0 + (long long)c * TN + wn * 32 + (j0 + jj) * 8 + g;
     if (ci >= n_cand) ci = n_cand - 1;  // tail tile: computed, never stored by finalize
 #pragma unroll
-    for (int k = 0; k < DMAX; ++k) cc[jj][k] = (k < d) ? (double)cand[ci * ldc + k] : 0.0;
+    for (int k = 0; k < D; ++k) cc[jj][k] = (k < d) ? (double)cand[ci * ldc + k] : 0.0;
   }
   double macc[MOBJ][2];
+  double coef[MOBJ], pvar[MOBJ];
 #pragma unroll
-  for (int o = 0; o < MOBJ; ++o) macc[o][0] = macc[o][1] = 0.0;
+  for (int o = 0; o < MOBJ; ++o) {
+    macc[o][0] = macc[o][1] = 0.0;
+    coef[o] = hp.neg_half_inv_ls2[o];
+    pvar[o] = hp.prior_var[o];
+  }
 
-  for (int kt = 0; kt < nkt; ++kt) {
+  for (int r0 = 0; r0 < npad; r0 += KS_ROWS) {
+    __syncthreads();  // previous block fully consumed (also orders the exp_tab fill)
+    for (int e = tid; e < KS_ROWS * (D + MOBJ); e += 128) {
+      const int r = e / (D + MOBJ), k = e - r * (D + MOBJ);
+      const int row = r0 + r;
+      double v = 0.0;
+      if (row < npad) {
+        const int rr = row < n ? row : n - 1;  // padded rows reuse the last real point (finite values)
+        if (k < D) v = (k < d) ? x[(long long)rr * ldx + k] : 0.0;
+        else v = alpha[(long long)(k - D) * npad + row];
+      }
+      xs[r][k] = v;
+    }
+    __syncthreads();
+    const int kt_end = min(nkt, (r0 + KS_ROWS) / TK);
+    for (int kt = r0 / TK; kt < kt_end; ++kt) {
 #pragma unroll
-    for (int sp = 0; sp < 2; ++sp) {
-      double val[MOBJ][2][2];  // [o][jj][q]
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int e = kt * TK + (sp * 2 + q) * 4 + t;
-        const bool live = e < n;
-        const int er = live ? e : 0;
-        double xe[DMAX];
-#pragma unroll
-        for (int k = 0; k < DMAX; ++k) xe[k] = (k < d) ? __ldg(x + (long long)er * ldx + k) : 0.0;
-        double al[MOBJ];
-#pragma unroll
-        for (int o = 0; o < MOBJ; ++o) al[o] = __ldg(alpha + (long long)o * npad + er);
+      for (int sp = 0; sp < 2; ++sp) {
+        const double* xa = xs[kt * TK - r0 + (sp * 2 + 0) * 4 + t];
+        const double* xb = xs[kt * TK - r0 + (sp * 2 + 1) * 4 + t];
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
-          double sq = 0.0;
+          double sa = 0.0, sb = 0.0;
 #pragma unroll
-          for (int k = 0; k < DMAX; ++k) {
-            if (k < d) {
-              const double diff = xe[k] - cc[jj][k];
-              sq = fma(diff, diff, sq);
-            }
+          for (int k = 0; k < D; ++k) {
+            const double da = xa[k] - cc[jj][k];
+            const double db = xb[k] - cc[jj][k];
+            sa = fma(da, da, sa);
+            sb = fma(db, db, sb);
           }
 #pragma unroll
           for (int o = 0; o < MOBJ; ++o) {
-            const double v = live ? hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]) : 0.0;
-            val[o][jj][q] = v;
-            macc[o][jj] = fma(v, al[o], macc[o][jj]);
+            const double va = pvar[o] * rbf_exp(sa * coef[o], exp_tab);
+            const double vb = pvar[o] * rbf_exp(sb * coef[o], exp_tab);
+            macc[o][jj] = fma(va, xa[D + o], macc[o][jj]);
+            macc[o][jj] = fma(vb, xb[D + o], macc[o][jj]);
+            double* dst = Kp + (((long long)o * chunk_tiles + c) * nkt + kt) * TILE_DOUBLES +
+                          ((wn * 4 + j0 + jj) * 2 + sp) * 64 + lane * 2;
+            *reinterpret_cast<double2*>(dst) = make_double2(va, vb);
           }
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < MOBJ; ++o) {
-        double* tile = Kp + (((long long)o * chunk_tiles + c) * nkt + kt) * TILE_DOUBLES;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          double* dst = tile + ((wn * 4 + j0 + jj) * 2 + sp) * 64 + lane * 2;
-          *reinterpret_cast<double2*>(dst) = make_double2(val[o][jj][0], val[o][jj][1]);
         }
       }
     }
@@ -330,14 +347,17 @@ template <typename CT>
 int launch_kstar(int m, int d, dim3 grid, cudaStream_t st, double* Kp, double* meandot, const CT* cand, int ldc,
                  long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x, int ldx,
                  int n, int npad, const double* alpha, const ObjParams& hp) {
-  if (d <= 4)
-    return launch_kstar_m<CT, 4>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
-                                 npad, d, alpha, hp);
-  if (d <= 8)
-    return launch_kstar_m<CT, 8>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
-                                 npad, d, alpha, hp);
-  return launch_kstar_m<CT, 16>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n,
-                                npad, d, alpha, hp);
+#define BO_KD(DD)                                                                                                  \
+  return launch_kstar_m<CT, DD>(m, grid, st, Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, \
+                                n, npad, d, alpha, hp)
+  if (d <= 2) BO_KD(2);
+  if (d <= 4) BO_KD(4);
+  if (d <= 6) BO_KD(6);
+  if (d <= 8) BO_KD(8);
+  if (d <= 10) BO_KD(10);
+  if (d <= 12) BO_KD(12);
+  BO_KD(16);
+#undef BO_KD
 }
 
 }  // namespace
@@ -434,7 +454,14 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
   const int npairs = (p.nb + 1) / 2;
   const long long n_chunks = (n_cand + p.ld_chunk - 1) / p.ld_chunk;
 
-  Overlap* ov = (p.nbuf == 2) ? overlap_for_current_device() : nullptr;
+  // Generating K*(i+1) on the helper stream while TRMM(i) runs is OPT-IN (BO_SCORE_OVERLAP=1): DMMA and
+  // DFMA share one FP64 datapath on B200, so there is nothing to hide behind, and co-resident K* CTAs
+  // delay the launch of the 48K-register TRMM CTAs (measured: 71.4 ms overlapped vs 68.3 ms serial).
+  static const bool want_overlap = [] {
+    const char* e = getenv("BO_SCORE_OVERLAP");
+    return e && e[0] == '1';
+  }();
+  Overlap* ov = (p.nbuf == 2 && want_overlap) ? overlap_for_current_device() : nullptr;
   cudaStream_t ks_stream = ov ? ov->aux : stream;
   if (ov) {
     BO_CUDA(cudaEventRecord(ov->inputs_ready, stream));  // factor / candidates produced on the caller's stream
