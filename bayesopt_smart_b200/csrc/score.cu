@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(128, 4)
                       const double* __restrict__ x, int ldx, int n, int npad, int d, const double* __restrict__ alpha,
                       ObjParams hp) {
   __shared__ double exp_tab[64];
-  __shared__ double xs[KS_ROWS][D + MOBJ];  // row: D coordinates then MOBJ alphas
+  // row: D coordinates then MOBJ alphas; odd row stride keeps the 4 rows a warp reads (t = 0..3) in
+  // different banks
+  __shared__ double xs[KS_ROWS][(D + MOBJ) | 1];
   const int tid = threadIdx.x;
   if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
   const int c = blockIdx.x >> 1;

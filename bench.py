@@ -327,6 +327,15 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu capture of the same kernel / workload
+        with open(os.path.join(ROOT, "profiles", "trmm_traffic.json")) as f:
+            tr = json.load(f)
+        if tr["n_train"] == n and tr["objectives"] == m:
+            traffic = {"bytes_per_launch": tr["dram_bytes_per_launch"],
+                       "candidates_per_launch": tr["candidates_per_launch"], "source": "profiles/trmm_traffic.json"}
+    except (OSError, KeyError, ValueError):
+        pass
     total_cands = n_cand * world * args.steps
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
     # bounded CPU sample of the same workload (reference port), ~10-20 s
@@ -353,7 +362,7 @@ def run_gpu_arm(args):
                 "api": "engine.hot_path_iteration (pinned host x, y, input_space in; mu, var, acq, batch out)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "trmm_sumsq_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tflops,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None, "traffic": traffic,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is absent from "
                                     "MEASURED_PEAKS.json; nominal B200 FP64 tensor 37-40 TFLOP/s)",
                      "algorithmic": "m*N^2 flop per candidate = 2.097e6; per launch x candidates in the chunk",

@@ -1,0 +1,51 @@
+"""Summarise ncu outputs into the text/CSV files kept under profiles/.
+    python tools/ncu_summary.py launches <csv>             -> per-kernel totals and shares
+    python tools/ncu_summary.py raw <file.ncu-rep>         -> the roofline-relevant counters per launch
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_src_fp64.sum.per_second", "sm__ops_path_tensor_src_fp64.sum.peak_sustained_elapsed.per_second",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__cycles_elapsed.avg", "smsp__inst_executed.sum"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for row in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        name = re.sub(r"^void ", "", name).replace("bo::<unnamed>::", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"total {tot:.1f} us over {sum(v[0] for v in agg.values())} launches")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1]:12.1f} us {100 * v[1] / tot:5.1f}%  n={v[0]:4d} avg={v[1] / v[0]:9.1f} us  {k[:100]}")
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(out.splitlines()))
+    hdr, units, rows = r[0], r[1], r[2:]
+    names = [row[hdr.index("Kernel Name")][:60] for row in rows]
+    print("kernels:", names)
+    for i, h in enumerate(hdr):
+        if h in KEYS:
+            print(f"{h} [{units[i]}]: {[row[i] for row in rows]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
