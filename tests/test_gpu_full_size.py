@@ -1,0 +1,154 @@
+"""BASELINE.json configs at FULL size on one B200, checked through size-independent properties and oracle
+spot checks (the oracle cannot run these sizes in full): shard/merge invariance of the top-k, a strided sample
+against the CPU oracle, exclusion of evaluated rows, Pareto front closure, MLL determinism.
+Multi-GPU configs are exercised as one rank's shard (the path has no data-path collective)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import bayesopt_smart_b200 as p
+
+    return p
+
+
+def _spot_check(gp, out, cand_dev, x, y, mu0, var0, ls, n, m, count, tau):
+    sel = torch.arange(0, cand_dev.shape[0], max(1, cand_dev.shape[0] // count), device="cuda")[:count]
+    cs = cand_dev[sel].cpu().numpy()
+    fit = orc.chol_fit(x, y, mu0, var0, ls, n)
+    mu_o, var_o = orc.chol_predict(fit, x, cs, mu0, var0, ls, n)
+    for o in range(m):
+        assert np.abs(out["mu"][o][sel].cpu().numpy() - mu_o[o]).max() / np.sqrt(var0[o]) <= tau
+        assert np.abs(out["var"][o][sel].cpu().numpy() - var_o[o]).max() / var0[o] <= tau
+
+
+def test_cfg2_full_grid(pkg):
+    """cfg2: ZDT1 d=6, N=1024, the full 10^6-point grid linspace(0,1,10)^6, 2 objectives, 1 GPU."""
+    from bayesopt_smart_b200.engine import DeviceGP, to_device
+
+    n, d, m = 1024, 6, 2
+    x, y, mu0, var0 = orc.make_training_set("zdt1", n, d, seed=0)
+    axes = [np.linspace(0.0, 1.0, 10)] * d
+    cand = np.stack([g.ravel() for g in np.meshgrid(*axes, indexing="ij")], axis=-1)
+    cand[123456] = x[7]  # one grid point replaced by an evaluated point
+    ls, betas = np.full(m, 0.3), np.full(m, 2.0)
+    gp = DeviceGP()
+    gp.fit(x, y, mu0, var0, ls, n)
+    cd = to_device(cand)
+    out = gp.score(cd, betas, want=("mu", "var", "acq"))
+    _spot_check(gp, out, cd, x, y, mu0, var0, ls, n, m, 1200, 1e-9)
+    assert torch.isfinite(out["acq"]).all()
+    assert out["var"].min().item() >= 1e-10
+    for o in range(m):
+        assert out["var"][o].max().item() <= var0[o] * (1 + 1e-12)
+        # at the evaluated point the variance collapses to ~jitter level and the mean interpolates y
+        assert out["var"][o][123456].item() <= 1e-4 * var0[o]
+        assert abs(out["mu"][o][123456].item() - y[7, o]) <= 1e-4 * np.sqrt(var0[o])
+    # top-k: single shot == merge of 4 shards' lists (what the multi-GPU path does)
+    k = 19
+    sv, si = gp.topk(out["acq"], k)
+    parts = [gp.topk(out["acq"][lo:lo + 250_000], k, index_base=lo) for lo in range(0, 1_000_000, 250_000)]
+    mv, mi = gp.topk_merge(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), k)
+    assert torch.equal(si, mi) and torch.equal(sv, mv)
+    a = out["acq"].cpu().numpy()
+    assert np.array_equal(si.cpu().numpy(), orc.ranked_indices(a)[:k])
+    assert np.all(np.diff(sv.cpu().numpy()) <= 0)
+    # sharded scoring is bit-identical to the single pass
+    half = gp.score(cd[500_000:], betas, want=("acq",))
+    assert torch.equal(half["acq"], out["acq"][500_000:])
+    _, idx = gp.select(cd, out["acq"], to_device(x), 3)
+    assert 123456 not in idx.tolist() and len(set(idx.tolist())) == 3
+
+
+def test_cfg3_shard_n4096_d10(pkg):
+    """cfg3: ZDT2 d=10, N=4096, random candidates; one rank's work at reduced candidate count (the per-candidate
+    arithmetic does not depend on M), oracle spot check of 200 candidates."""
+    from bayesopt_smart_b200.engine import DeviceGP
+
+    n, d, m = 4096, 10, 2
+    x, y, mu0, var0 = orc.make_training_set("zdt2", n, d, seed=0)
+    ls, betas = np.full(m, 0.5), np.full(m, 2.0)
+    gp = DeviceGP()
+    gp.fit(x, y, mu0, var0, ls, n)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    cd = torch.rand(100_000, d, dtype=torch.float64, device="cuda", generator=g)
+    out = gp.score(cd, betas, want=("mu", "var", "acq"))
+    _spot_check(gp, out, cd, x, y, mu0, var0, ls, n, m, 200, 1e-9)  # cond ~ 1e5 at these hyper-parameters
+    assert torch.isfinite(out["acq"]).all()
+
+
+def test_cfg4_shard_three_objectives_hvi_pareto(pkg):
+    """cfg4: DTLZ2 d=8, N=2048, 3 objectives: scores, exact 3-objective HVI and Pareto filter of the UCB vectors."""
+    from bayesopt_smart_b200.acquisition import exact_hvi_device
+    from bayesopt_smart_b200.engine import DeviceGP
+    from bayesopt_smart_b200.pareto import pareto_mask_device
+
+    n, d, m = 2048, 8, 3
+    x, y, mu0, var0 = orc.make_training_set("dtlz2", n, d, seed=0)
+    ls, betas = np.full(m, 0.5), np.full(m, 2.0)
+    gp = DeviceGP()
+    gp.fit(x, y, mu0, var0, ls, n)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cd = torch.rand(200_000, d, dtype=torch.float64, device="cuda", generator=g)
+    out = gp.score(cd, betas, want=("mu", "var", "ucb", "acq"))
+    cond = max(np.linalg.cond(orc.chol_fit(x, y, mu0, var0, ls, n)["kernel"][o] + 1e-6 * np.eye(n)) for o in range(m))
+    _spot_check(gp, out, cd, x, y, mu0, var0, ls, n, m, 300, max(1e-9, 10 * EPS * cond))
+    y_std = (y - mu0) / np.sqrt(var0)
+    front = y_std[orc.pareto_mask_definition(y_std)]
+    ref = y_std.min(axis=0) - 0.1
+    hv = exact_hvi_device(out["ucb"], front, ref)
+    sel = np.arange(0, 200_000, 1000)
+    want = orc.exact_hvi(out["ucb"][:, sel].T.cpu().numpy(), front, ref)
+    np.testing.assert_allclose(hv[sel].cpu().numpy(), want, rtol=1e-10, atol=1e-12)
+    rows = out["ucb"].T.contiguous()
+    mask = pareto_mask_device(rows).bool()
+    fr = rows[mask].cpu().numpy()
+    assert np.array_equal(orc.pareto_mask_definition(fr), np.ones(fr.shape[0], bool))  # front is non-dominated
+    dropped = rows[~mask][::97].cpu().numpy()
+    ge = np.all(fr[None, :, :] >= dropped[:, None, :], axis=2)
+    gt = np.any(fr[None, :, :] > dropped[:, None, :], axis=2)
+    assert np.all(np.any(ge & gt, axis=1))  # every dropped point has a dominator on the front
+
+
+def test_pareto_8m_points(pkg):
+    from bayesopt_smart_b200.pareto import pareto_mask_device
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    yv = torch.randn(8_000_000, 3, dtype=torch.float64, device="cuda", generator=g)
+    mask = pareto_mask_device(yv).bool()
+    front = yv[mask].cpu().numpy()
+    assert 10 < front.shape[0] < 5000
+    assert orc.pareto_mask_definition(front).all()
+    drop = yv[~mask][::4001].cpu().numpy()
+    ge = np.all(front[None, :, :] >= drop[:, None, :], axis=2)
+    gt = np.any(front[None, :, :] > drop[:, None, :], axis=2)
+    assert np.all(np.any(ge & gt, axis=1))
+    # idempotence: the front of the front is the front
+    assert pareto_mask_device(yv[mask].contiguous()).all()
+
+
+def test_cfg5_full_sweep(pkg):
+    """cfg5: 256 (length scale, jitter) settings at N=4096, d=6: finite, deterministic, and the jitter=1e-8
+    settings equal compute_mll (oracle) -- one of them is checked (6 s of CPU)."""
+    from bayesopt_smart_b200 import numba_kernels as nk
+
+    n, d, m = 4096, 6, 2
+    x, y, mu0, _ = orc.make_training_set("zdt1", n, d, seed=0)
+    ls = np.repeat(np.logspace(-1, 0.5, 16), 16)
+    jit = np.tile(np.logspace(-8, -2, 16), 16)
+    vals = nk.mll_batched(x, y, mu0, np.stack([ls, ls], axis=1), jit, n)
+    assert vals.shape == (256,) and np.isfinite(vals).all()
+    again = nk.mll_batched(x, y, mu0, np.stack([ls, ls], axis=1)[:32], jit[:32], n)
+    assert np.array_equal(again, vals[:32])  # bit-reproducible, independent of the batch composition
+    s = 5 * 16  # length scale 0.316, jitter 1e-8
+    want = orc.ref_compute_mll(x, y, np.zeros((m, n, n)), mu0, np.ones(m), np.full(m, ls[s]), n)
+    assert abs(vals[s] - want) <= 1e-7 * abs(want)
