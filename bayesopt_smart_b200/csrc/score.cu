@@ -306,24 +306,51 @@ __global__ void finalize_kernel(double* __restrict__ mu_out, double* __restrict_
   if (acq_out) acq_out[gi] = acq;
 }
 
-// stand-alone a6..a8 on existing arrays (HBM bound: reads 2m, writes up to 3m+1 doubles per candidate)
-__global__ void acquisition_kernel(double* __restrict__ smu_out, double* __restrict__ svar_out,
-                                   double* __restrict__ ucb_out, double* __restrict__ acq_out,
-                                   const double* __restrict__ mu_in, const double* __restrict__ var_in, long long ld,
-                                   long long n_cand, int m, ObjParams hp) {
+// stand-alone a6..a8 on existing arrays (HBM bound: reads 2m, writes up to 3m+1 doubles per candidate).
+// Two candidates per thread with 16-byte accesses; VEC = false is the unaligned / odd-length fallback.
+template <int MOBJ, bool VEC>
+__global__ void __launch_bounds__(256)
+    acquisition_kernel(double* __restrict__ smu_out, double* __restrict__ svar_out, double* __restrict__ ucb_out,
+                       double* __restrict__ acq_out, const double* __restrict__ mu_in,
+                       const double* __restrict__ var_in, long long ld, long long n_cand, ObjParams hp) {
+  double sd[MOBJ];
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) sd[o] = sqrt(hp.prior_var[o]);  // numba_kernels.py:565 (one sqrt per objective)
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += stride) {
-    double acq = 0.0;
-    for (int o = 0; o < m; ++o) {
-      const double smu = (mu_in[o * ld + i] - hp.prior_mean[o]) / sqrt(hp.prior_var[o]);
-      const double svar = var_in[o * ld + i] / hp.prior_var[o];
-      const double ucb = smu + hp.beta[o] * sqrt(fabs(svar));
-      acq = acq + ucb;
-      if (smu_out) smu_out[o * ld + i] = smu;
-      if (svar_out) svar_out[o * ld + i] = svar;
-      if (ucb_out) ucb_out[o * ld + i] = ucb;
+  const long long npair = VEC ? n_cand / 2 : n_cand;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npair; p += stride) {
+    if (VEC) {
+      const long long i = 2 * p;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        const double2 mu = *reinterpret_cast<const double2*>(mu_in + o * ld + i);
+        const double2 va = *reinterpret_cast<const double2*>(var_in + o * ld + i);
+        const double2 smu = make_double2((mu.x - hp.prior_mean[o]) / sd[o], (mu.y - hp.prior_mean[o]) / sd[o]);
+        const double2 svar = make_double2(va.x / hp.prior_var[o], va.y / hp.prior_var[o]);
+        const double2 ucb = make_double2(smu.x + hp.beta[o] * sqrt(fabs(svar.x)), smu.y + hp.beta[o] * sqrt(fabs(svar.y)));
+        a0 = a0 + ucb.x;
+        a1 = a1 + ucb.y;
+        if (smu_out) *reinterpret_cast<double2*>(smu_out + o * ld + i) = smu;
+        if (svar_out) *reinterpret_cast<double2*>(svar_out + o * ld + i) = svar;
+        if (ucb_out) *reinterpret_cast<double2*>(ucb_out + o * ld + i) = ucb;
+      }
+      if (acq_out) *reinterpret_cast<double2*>(acq_out + i) = make_double2(a0, a1);
+    } else {
+      const long long i = p;
+      double acq = 0.0;
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        const double smu = (mu_in[o * ld + i] - hp.prior_mean[o]) / sd[o];
+        const double svar = var_in[o * ld + i] / hp.prior_var[o];
+        const double ucb = smu + hp.beta[o] * sqrt(fabs(svar));
+        acq = acq + ucb;
+        if (smu_out) smu_out[o * ld + i] = smu;
+        if (svar_out) svar_out[o * ld + i] = svar;
+        if (ucb_out) ucb_out[o * ld + i] = ucb;
+      }
+      if (acq_out) acq_out[i] = acq;
     }
-    if (acq_out) acq_out[i] = acq;
   }
 }
 
@@ -535,10 +562,27 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
 int acquisition_only(double* smu, double* svar, double* ucb, double* acq, const double* mu, const double* var,
                      long long ld, long long n_cand, int m, const ObjParams& hp, cudaStream_t stream) {
   if (n_cand <= 0) return BO_OK;
-  long long blocks = (n_cand + 255) / 256;
-  const long long cap = 8LL * device_sm_count();
+  auto aligned = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; };
+  const bool vec = (ld % 2 == 0) && (n_cand % 2 == 0) && aligned(smu) && aligned(svar) && aligned(ucb) &&
+                   aligned(acq) && aligned(mu) && aligned(var);
+  const long long items = vec ? n_cand / 2 : n_cand;
+  long long blocks = (items + 255) / 256;
+  const long long cap = 32LL * device_sm_count();
   if (blocks > cap) blocks = cap;
-  acquisition_kernel<<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, acq, mu, var, ld, n_cand, m, hp);
+#define BO_ACQ(MO)                                                                                              \
+  do {                                                                                                          \
+    if (vec)                                                                                                    \
+      acquisition_kernel<MO, true><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, acq, mu, var, ld, n_cand, hp); \
+    else                                                                                                        \
+      acquisition_kernel<MO, false><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, acq, mu, var, ld, n_cand, hp); \
+  } while (0)
+  switch (m) {
+    case 1: BO_ACQ(1); break;
+    case 2: BO_ACQ(2); break;
+    case 3: BO_ACQ(3); break;
+    default: BO_ACQ(4); break;
+  }
+#undef BO_ACQ
   BO_LAUNCH_CHECK("acquisition_kernel");
   return BO_OK;
 }

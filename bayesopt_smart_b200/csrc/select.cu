@@ -8,6 +8,8 @@
 //   hvi_kernel          exact 2-/3-objective hypervolume improvement against a front held in shared memory.
 #include "select.cuh"
 
+#include <stdlib.h>
+
 namespace bo {
 
 namespace {
@@ -41,9 +43,23 @@ __device__ __forceinline__ double key_to_double(unsigned long long key) {
   return __longlong_as_double((long long)b);
 }
 
+// position of sample element e in the full array: one element per stride-wide window, at a hashed offset
+// (a plain stride would alias with periodic score patterns of Cartesian candidate grids)
+__device__ __forceinline__ long long sample_pos(long long e, int stride) {
+  const unsigned h = (unsigned)e * 2654435761u;
+  return e * stride + (long long)((h >> 8) % (unsigned)stride);
+}
+
+// sample_stride > 0: the input is the virtual array in_val[sample_pos(e)], e < n_in, positions >= n_total
+// are skipped.  n_in_dev != nullptr: the element count is read from device memory (clamped to n_in).
 __global__ void __launch_bounds__(SEL_THREADS)
     topk_slice_kernel(double* __restrict__ out_val, long long* __restrict__ out_idx, const double* __restrict__ in_val,
-                      const long long* __restrict__ in_idx, long long n_in, int k, long long index_base) {
+                      const long long* __restrict__ in_idx, long long n_in, int k, long long index_base,
+                      int sample_stride, long long n_total, const int* __restrict__ n_in_dev) {
+  if (n_in_dev) {
+    const long long cnt = *n_in_dev;
+    n_in = cnt < n_in ? cnt : n_in;
+  }
   __shared__ Best warp_best[SEL_THREADS / 32];
   __shared__ Best block_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -58,11 +74,14 @@ __global__ void __launch_bounds__(SEL_THREADS)
     keys[p] = 0ull;
     idxs[p] = -1;
     if (e < n_in) {
-      const long long id = in_idx ? in_idx[e] : index_base + e;
-      if (id >= 0) {
-        keys[p] = order_key(in_val[e]);
-        idxs[p] = id;
-        valid |= 1u << p;
+      const long long pos = sample_stride > 0 ? sample_pos(e, sample_stride) : e;
+      if (sample_stride == 0 || pos < n_total) {
+        const long long id = in_idx ? in_idx[pos] : index_base + pos;
+        if (id >= 0) {
+          keys[p] = order_key(in_val[pos]);
+          idxs[p] = id;
+          valid |= 1u << p;
+        }
       }
     }
   }
@@ -140,6 +159,43 @@ __global__ void match_rows_kernel(uint8_t* __restrict__ flag, const long long* _
   if (threadIdx.x == 0) flag[blockIdx.x] = (uint8_t)hit;
 }
 
+// Streaming filter of the top-k scan: keep every element that is not worse than the threshold element
+// (value desc, index asc order).  Survivors are appended with warp-aggregated atomics; their order is
+// irrelevant because the exact kernel that follows ranks by (value, index).
+__global__ void __launch_bounds__(256)
+    topk_filter_kernel(double* __restrict__ out_val, long long* __restrict__ out_idx, int* __restrict__ count,
+                       int capacity, const double* __restrict__ in_val, long long n, long long index_base,
+                       const double* __restrict__ thr_val, const long long* __restrict__ thr_idx) {
+  const unsigned long long key_t = order_key(*thr_val);
+  const long long idx_t = *thr_idx;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long rounds = (n + stride - 1) / stride;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long r = 0; r < rounds; ++r, i += stride) {
+    bool keep = false;
+    double v = 0.0;
+    if (i < n) {
+      v = in_val[i];
+      const unsigned long long key = order_key(v);
+      keep = key > key_t || (key == key_t && index_base + i <= idx_t);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (mask) {
+      int base = 0;
+      if (lane == __ffs(mask) - 1) base = atomicAdd(count, __popc(mask));
+      base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+      if (keep) {
+        const int slot = base + __popc(mask & ((1u << lane) - 1));
+        if (slot < capacity) {
+          out_val[slot] = v;
+          out_idx[slot] = index_base + i;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- Pareto
 constexpr int PAR_TILE = 1024;
 
@@ -161,9 +217,12 @@ __global__ void __launch_bounds__(256)
       for (int o = 0; o < MOBJ; ++o) zs[o][e] = z[(j0 + e) * ldz + o];
     }
     __syncthreads();
-    // warp-ballot early-out: a warp whose 32 points are all already dominated skips the tile
-    if (__ballot_sync(0xffffffffu, !dominated) != 0u) {
-      for (int j = 0; j < cnt; ++j) {
+    // warp-ballot early-out, re-evaluated every 16 rows of z: a warp whose 32 points are all already
+    // dominated stops comparing (callers put the strongest rows of z first)
+    for (int jb = 0; jb < cnt; jb += 16) {
+      if (__ballot_sync(0xffffffffu, !dominated) == 0u) break;
+      const int je = min(cnt, jb + 16);
+      for (int j = jb; j < je; ++j) {
         bool ge = true, gt = false;
 #pragma unroll
         for (int o = 0; o < MOBJ; ++o) {
@@ -252,19 +311,27 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 // =========================================================================================== host drivers
-size_t topk_workspace_bytes(long long n_cand, int k) {
-  const long long blocks0 = (n_cand + SEL_SLICE - 1) / SEL_SLICE;
+constexpr int FILTER_CAPACITY = 1 << 16;      // survivor pairs of the filtered scan
+constexpr long long FILTER_MIN_N = 1 << 18;   // below this the plain multi-level scan is used
+constexpr int FILTER_MAX_K = 256;
+
+static size_t levels_bytes(long long n_in, int k) {
+  const long long blocks0 = (n_in + SEL_SLICE - 1) / SEL_SLICE;
   const size_t pairs = (size_t)(blocks0 > 0 ? blocks0 : 1) * (size_t)k;
-  // two ping-pong (value, index) buffers
   return 2 * (align256(pairs * sizeof(double)) + align256(pairs * sizeof(long long)));
 }
 
-int topk_levels(double* out_val, long long* out_idx, const double* val, const long long* idx, long long n_in, int k,
-                long long index_base, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (workspace_bytes < topk_workspace_bytes(n_in, k)) {
-    set_error("top-k workspace too small");
-    return BO_ERR_WORKSPACE;
-  }
+size_t topk_workspace_bytes(long long n_cand, int k) {
+  // multi-level ping-pong buffers + survivor list + threshold pair + counter
+  return levels_bytes(n_cand, k) + align256(FILTER_CAPACITY * sizeof(double)) +
+         align256(FILTER_CAPACITY * sizeof(long long)) + align256((size_t)k * sizeof(double)) +
+         align256((size_t)k * sizeof(long long)) + 256;
+}
+
+// stride > 0: first level reads the hashed sample of `val` (n_in = number of sample elements)
+static int topk_levels_impl(double* out_val, long long* out_idx, const double* val, const long long* idx,
+                            long long n_in, int k, long long index_base, int stride, long long n_total,
+                            const int* n_in_dev, void* workspace, cudaStream_t stream) {
   const long long blocks0 = (n_in + SEL_SLICE - 1) / SEL_SLICE;
   const size_t pairs = (size_t)(blocks0 > 0 ? blocks0 : 1) * (size_t)k;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -281,21 +348,68 @@ int topk_levels(double* out_val, long long* out_idx, const double* val, const lo
   const long long* cur_i = idx;
   long long cur_n = n_in;
   int buf = 0;
+  bool first = true;
   while (true) {
     long long blocks = (cur_n + SEL_SLICE - 1) / SEL_SLICE;
     if (blocks < 1) blocks = 1;
     const bool last = blocks == 1;
     double* ov = last ? out_val : v[buf];
     long long* oi = last ? out_idx : ix[buf];
-    topk_slice_kernel<<<(unsigned)blocks, SEL_THREADS, 0, stream>>>(ov, oi, cur_v, cur_i, cur_n, k, index_base);
+    topk_slice_kernel<<<(unsigned)blocks, SEL_THREADS, 0, stream>>>(ov, oi, cur_v, cur_i, cur_n, k, index_base,
+                                                                    first ? stride : 0, n_total,
+                                                                    first ? n_in_dev : nullptr);
     BO_LAUNCH_CHECK("topk_slice_kernel");
     if (last) break;
     cur_v = ov;
     cur_i = oi;
     cur_n = blocks * k;
     buf ^= 1;
+    first = false;
   }
   return BO_OK;
+}
+
+int topk_levels(double* out_val, long long* out_idx, const double* val, const long long* idx, long long n_in, int k,
+                long long index_base, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < topk_workspace_bytes(n_in, k)) {
+    set_error("top-k workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  static const bool no_filter = [] {
+    const char* e = getenv("BO_TOPK_NO_FILTER");
+    return e && e[0] == '1';
+  }();
+  if (idx == nullptr && n_in >= FILTER_MIN_N && k <= FILTER_MAX_K && !no_filter) {
+    // --- filtered scan: threshold from a hashed sample, one streaming pass, exact top-k of the survivors ---
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    size_t off = levels_bytes(n_in, k);
+    double* sv = reinterpret_cast<double*>(ws + off);       off += align256(FILTER_CAPACITY * sizeof(double));
+    long long* si = reinterpret_cast<long long*>(ws + off); off += align256(FILTER_CAPACITY * sizeof(long long));
+    double* tv = reinterpret_cast<double*>(ws + off);       off += align256((size_t)k * sizeof(double));
+    long long* ti = reinterpret_cast<long long*>(ws + off); off += align256((size_t)k * sizeof(long long));
+    int* count = reinterpret_cast<int*>(ws + off);
+    int stride = 16384 / k;  // expected survivors ~ k * stride = 16384 << capacity
+    if (stride > 256) stride = 256;
+    if (stride < 2) stride = 2;
+    const long long n_sample = (n_in + stride - 1) / stride;
+    int rc = topk_levels_impl(tv, ti, val, nullptr, n_sample, k, index_base, stride, n_in, nullptr, workspace,
+                              stream);
+    if (rc) return rc;
+    BO_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
+    long long blocks = (n_in + 256 * 8 - 1) / (256 * 8);
+    const long long cap = 16LL * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    topk_filter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(sv, si, count, FILTER_CAPACITY, val, n_in, index_base,
+                                                             tv + (k - 1), ti + (k - 1));
+    BO_LAUNCH_CHECK("topk_filter_kernel");
+    int count_h = 0;
+    BO_CUDA(cudaMemcpyAsync(&count_h, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BO_CUDA(cudaStreamSynchronize(stream));
+    if (count_h >= k && count_h <= FILTER_CAPACITY)
+      return topk_levels_impl(out_val, out_idx, sv, si, count_h, k, 0, 0, 0, nullptr, workspace, stream);
+    // threshold unusable (fewer than k valid sample elements, NaN threshold, massive ties): exact fallback
+  }
+  return topk_levels_impl(out_val, out_idx, val, idx, n_in, k, index_base, 0, 0, nullptr, workspace, stream);
 }
 
 int match_rows(uint8_t* flag, const long long* idx, int n_idx, long long index_base, const void* cand, int cand_kind,

@@ -51,7 +51,11 @@ def pareto_mask_device(y: torch.Tensor) -> torch.Tensor:
             break
         step = max(1, cur.shape[0] // _SAMPLE)
         sample = cur[::step].contiguous()
-        front = sample[_mask_direct(sample).bool()].contiguous()
+        front = sample[_mask_direct(sample).bool()]
+        # strongest points first: most rows are then dominated within the first few comparisons and
+        # their warps leave the loop early (ordering only; NaN sums go last)
+        order = torch.argsort(torch.nan_to_num(front.sum(dim=1), nan=float("-inf")), descending=True)
+        front = front[order].contiguous()
         keep = _mask_against(cur, front).bool()
         if keep.all():
             break

@@ -121,7 +121,10 @@ int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev,
 
 /* ------------------------------------------------------------ a9: select_next_batch
  * Top-k of acq (value descending, index ascending on ties, NaN last).  Writes k
- * (value, index + index_base) pairs sorted best-first.  k <= BO_MAX_TOPK.
+ * (value, index + index_base) pairs sorted best-first.  k <= BO_MAX_TOPK.  For n_cand >= 2^18 and
+ * k <= 256 the scan is: exact top-k of a hashed 1/stride sample -> its k-th element is a lower bound of
+ * the true k-th best -> one streaming filter pass -> exact top-k of the survivors (synchronises once to
+ * read the survivor count; falls back to the plain multi-level scan if they overflow).
  * bo_match_rows_f64 flags, for each listed candidate row, whether it equals (==, all
  * d coordinates) some evaluated row x[0:n): the exclusion test of acquisition.py:139.
  * Replaces the argsort + walk of select_next_batch, acquisition.py:116-144.        */

@@ -297,6 +297,40 @@ def test_topk_matches_total_order(pkg):
         np.testing.assert_array_equal(vals.cpu().numpy(), a[order])
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "periodic", "ascending", "descending", "mostly_nan", "top_ties",
+                                  "all_nan"])
+def test_topk_filtered_scan_adversarial(pkg, kind):
+    """Large inputs take the sampled-threshold + streaming-filter path; these inputs stress the threshold
+    (massive ties, periodic patterns aligned with grids, NaNs) and must still equal the total order."""
+    from bayesopt_smart_b200.engine import DeviceGP
+
+    n = 700_003
+    rng = np.random.default_rng(1)
+    if kind == "all_equal":
+        a = np.full(n, 0.25)
+    elif kind == "periodic":
+        a = np.tile(np.array([0.0] * 63 + [1.0]), n // 64 + 1)[:n] + 1e-9 * (np.arange(n) % 1000)
+    elif kind == "ascending":
+        a = np.arange(n, dtype=np.float64)
+    elif kind == "descending":
+        a = -np.arange(n, dtype=np.float64)
+    elif kind == "mostly_nan":
+        a = np.full(n, np.nan)
+        a[rng.choice(n, 500, replace=False)] = rng.normal(size=500)
+    elif kind == "top_ties":
+        a = rng.normal(size=n)
+        a[rng.choice(n, 5000, replace=False)] = 10.0
+    else:
+        a = np.full(n, np.nan)
+    gp = DeviceGP()
+    t = torch.from_numpy(a).cuda()
+    for k in (3, 19, 200):
+        vals, idx = gp.topk(t, k, index_base=7)
+        order = orc.ranked_indices(a)[:k]
+        assert np.array_equal(idx.cpu().numpy() - 7, order), (kind, k)
+        np.testing.assert_array_equal(vals.cpu().numpy(), a[order])
+
+
 def test_select_skips_evaluated_rows_and_exhaustion(pkg):
     from bayesopt_smart_b200 import acquisition as aq
 
