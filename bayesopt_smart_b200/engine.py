@@ -53,7 +53,8 @@ class _Workspace:
 
 
 def to_device(a, dtype=None, device=None) -> torch.Tensor:
-    """numpy / torch -> contiguous CUDA tensor (pinned staging for host arrays)."""
+    """numpy / torch -> contiguous CUDA tensor.  Host tensors that are already pinned copy asynchronously;
+    NumPy arrays go through the driver's own staging (pinning per call would cost more than it saves)."""
     device = device or require_cuda()
     if isinstance(a, torch.Tensor):
         t = a.to(device=device, dtype=dtype or a.dtype)
@@ -61,12 +62,7 @@ def to_device(a, dtype=None, device=None) -> torch.Tensor:
     arr = np.ascontiguousarray(a)
     if dtype is not None:
         arr = arr.astype({torch.float64: np.float64, torch.int64: np.int64}[dtype], copy=False)
-    t = torch.from_numpy(arr)
-    try:
-        t = t.pin_memory()
-    except RuntimeError:
-        pass
-    return t.to(device, non_blocking=True)
+    return torch.from_numpy(arr).to(device)
 
 
 def candidate_kind(cand: torch.Tensor) -> int:
