@@ -1,229 +1,186 @@
-"""Drop-in for the reference's ``bayesopt/bayesian_optimization.py``: same class, constructor
-kwargs, public attributes, ``optimize()`` / ``pareto_analysis()`` and callback contract; the
-per-iteration hot path runs device-resident through :class:`engine.DeviceGP`.
+"""Drop-in for the reference's ``bayesopt/bayesian_optimization.py``.
+
+Public surface kept: ``BayesianOptimization(function, bounds, n_objectives, n_iterations,
+**kwargs)`` with the same kwargs and attributes, ``.optimize()``, ``.pareto_analysis()``, the module-level
+``optimize(...)`` with the reference's 23 parameters, and the ``callback(state)`` hook with identical keys.
+What differs is where the work happens: the per-iteration hot path (reference :129-207) runs device-resident
+through :class:`bayesopt_smart_b200.engine.DeviceGP`.
 """
 from __future__ import annotations
 
 import time
-from typing import Any, Callable, List, Optional, Tuple
 
 import numpy as np
 import torch
 
+from . import config as cfg
 from .acquisition import exact_hvi_device
-from .config import (
-    DEFAULT_BATCH_SIZE,
-    DEFAULT_BETA,
-    DEFAULT_INITIAL_SAMPLES,
-    DEFAULT_LENGTH_SCALE,
-    DEFAULT_PRIOR_MEAN,
-    DEFAULT_PRIOR_VARIANCE,
-    NUMBA_FLOAT_TYPE,
-)
 from .engine import DeviceGP, PinnedMirror, require_cuda, to_device
-from .numba_kernels import (
-    compute_prior_mean,
-    compute_prior_variance,
-    initialize_lhs_integer,
-    optimize_hyperparams_mll,
-)
+from .numba_kernels import (compute_prior_mean, compute_prior_variance, initialize_lhs_integer,
+                            optimize_hyperparams_mll)
 from .pareto import compute_pareto_front, is_pareto_efficient, print_pareto_analysis
 
+# device result key -> name of the host buffer the reference keeps for it
+_HOST_BUFFERS = {"mu": "mu_objectives", "var": "variance_objectives", "std_mu": "std_mu_objectives",
+                 "std_var": "std_variance_objectives", "ucb": "ucb", "acq": "acquisition_values"}
+_TIMING_KEYS = ("hyperparams", "kernels", "acquisition", "eval", "total")
 
-def optimize(
-    x_vector: np.ndarray,
-    y_vector: np.ndarray,
-    kernel_matrices: np.ndarray,
-    k_star: np.ndarray,
-    mu_objectives: np.ndarray,
-    variance_objectives: np.ndarray,
-    std_mu_objectives: np.ndarray,
-    std_variance_objectives: np.ndarray,
-    ucb: np.ndarray,
-    acquisition_values: np.ndarray,
-    input_space: np.ndarray,
-    prior_mean: np.ndarray,
-    prior_variance: np.ndarray,
-    reference_point: np.ndarray,
-    n_evaluations: int,
-    total_samples: int,
-    n_objectives: int,  # pylint: disable=unused-argument
-    function: Callable[[np.ndarray], np.ndarray],
-    betas: np.ndarray,
-    length_scales: np.ndarray,
-    batch_size: int,
-    bounds: List[Tuple[int, int]],  # pylint: disable=unused-argument
-    callbacks: Optional[List[Callable]] = None,
-    acquisition: str = "sum_ucb",
-) -> Tuple[np.ndarray, np.ndarray, int]:
-    """The BO loop.  Reference bayesian_optimization.py:51-247 (same parameters, same return).
 
-    Per iteration: Powell fit of the hyper-parameters on the GPU MLL, ``DeviceGP.fit`` (Gram +
-    Cholesky + W = L^-1 + alpha), ``DeviceGP.score`` over the resident candidate set,
-    ``DeviceGP.select``.  The host arrays ``mu_objectives`` .. ``acquisition_values`` are refreshed
-    every iteration when callbacks are installed (they receive NumPy arrays) and once at the end
-    otherwise.  ``kernel_matrices`` and ``k_star`` are accepted for signature compatibility and left
-    untouched: K* is never materialised.  ``acquisition="exact_hvi"`` (opt-in, 2 or 3 objectives)
-    replaces the reference's sum-UCB score by the exact hypervolume improvement of the UCB vector
-    against the current standardised front, with ``reference_point`` as lower corner.
-    Returns ``(x_vector, y_vector, last_eval + 1)`` like the reference (:247).
+class _Clock:
+    """perf_counter stamps t0..t4 of one iteration -> the reference's ``timings`` dict (:236-242)."""
+
+    def __init__(self):
+        self.marks = [time.perf_counter()]
+
+    def tick(self):
+        self.marks.append(time.perf_counter())
+
+    def timings(self):
+        t = self.marks
+        spans = [t[i + 1] - t[i] for i in range(4)] + [t[4] - t[0]]
+        return dict(zip(_TIMING_KEYS, spans))
+
+
+def _exact_hvi_scores(out, y_seen, prior_mean, prior_variance, reference_point):
+    """Opt-in acquisition: exact HVI of each UCB vector against the standardised observed front."""
+    scale = np.sqrt(prior_variance)
+    y_std = (y_seen - prior_mean) / scale
+    front = y_std[is_pareto_efficient(y_std)]
+    ref_std = np.minimum((np.asarray(reference_point, dtype=np.float64) - prior_mean) / scale, y_std.min(axis=0))
+    return exact_hvi_device(out["ucb"], front, ref_std)
+
+
+def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, variance_objectives, std_mu_objectives,
+             std_variance_objectives, ucb, acquisition_values, input_space, prior_mean, prior_variance,
+             reference_point, n_evaluations, total_samples, n_objectives, function, betas, length_scales,
+             batch_size, bounds, callbacks=None, acquisition="sum_ucb"):
+    """The BO loop; same parameters and return value as the reference (:51-247).
+
+    Each iteration: Powell fit of (length_scales, prior_variance) on the GPU log marginal likelihood,
+    ``DeviceGP.fit`` (Gram, Cholesky, W = L^-1, alpha), ``DeviceGP.score`` over the resident candidates,
+    ``DeviceGP.select``, objective evaluation, callbacks.  Host copies of the per-candidate arrays are
+    refreshed every iteration when callbacks are installed (they get NumPy arrays, as in the reference) and
+    once after the last iteration otherwise.  ``kernel_matrices`` / ``k_star`` are accepted and left
+    untouched (K* is never materialised).  ``acquisition="exact_hvi"`` swaps the reference's sum-UCB score
+    for the exact hypervolume improvement (2 or 3 objectives).  Returns ``(x_vector, y_vector,
+    last_eval + 1)`` -- the reference's own off-by-batch quirk (:247).
     """
-    dev = require_cuda()
-    gp = DeviceGP(dev)
-    cand_dev = to_device(input_space, None, dev)  # uploaded once, resident for the whole run
-    n_cand = cand_dev.shape[0]
-    m = y_vector.shape[1]
-    keys = ("mu", "var", "std_mu", "std_var", "ucb", "acq")
-    out = {k: torch.empty((n_cand,) if k == "acq" else (m, n_cand), dtype=torch.float64, device=dev) for k in keys}
-    host = dict(mu=mu_objectives, var=variance_objectives, std_mu=std_mu_objectives, std_var=std_variance_objectives,
-                ucb=ucb, acq=acquisition_values)
-    mirror = PinnedMirror()
+    device = require_cuda()
+    gp = DeviceGP(device)
+    candidates = to_device(input_space, None, device)  # uploaded once, stays in HBM
+    n_cand, m = candidates.shape[0], y_vector.shape[1]
+    out = {k: torch.empty((n_cand,) if k == "acq" else (m, n_cand), dtype=torch.float64, device=device)
+           for k in _HOST_BUFFERS}
+    host = dict(mu=mu_objectives, var=variance_objectives, std_mu=std_mu_objectives,
+                std_var=std_variance_objectives, ucb=ucb, acq=acquisition_values)
+    staging = PinnedMirror()
+    starts = range(n_evaluations, total_samples, batch_size)
     last_eval = 0
-    iterations = list(range(n_evaluations, total_samples, batch_size))
-    for current_eval in iterations:
-        iter_start = time.perf_counter()
-        t0 = time.perf_counter()
-        optimized_hyperparams = optimize_hyperparams_mll(
-            x_vector=x_vector, y_vector=y_vector, kernel_matrix=kernel_matrices, prior_mean=prior_mean,
-            prior_variance=prior_variance, length_scales=length_scales, current_eval=current_eval)
-        t1 = time.perf_counter()
 
-        gp.fit(x_vector[:current_eval], y_vector[:current_eval], prior_mean, prior_variance, length_scales,
-               current_eval)
+    for current_eval in starts:
+        clock = _Clock()
+        fitted = optimize_hyperparams_mll(x_vector=x_vector, y_vector=y_vector, kernel_matrix=kernel_matrices,
+                                          prior_mean=prior_mean, prior_variance=prior_variance,
+                                          length_scales=length_scales, current_eval=current_eval)
+        clock.tick()
+
+        seen_x, seen_y = x_vector[:current_eval], y_vector[:current_eval]
+        gp.fit(seen_x, seen_y, prior_mean, prior_variance, length_scales, current_eval)
         torch.cuda.synchronize()
-        t2 = time.perf_counter()
+        clock.tick()
 
-        gp.score(cand_dev, betas, out=out)
+        gp.score(candidates, betas, out=out)
         score = out["acq"]
         if acquisition == "exact_hvi":
-            y_std = (y_vector[:current_eval] - prior_mean) / np.sqrt(prior_variance)
-            front = y_std[is_pareto_efficient(y_std)]
-            ref_std = (np.asarray(reference_point, dtype=np.float64) - prior_mean) / np.sqrt(prior_variance)
-            ref_std = np.minimum(ref_std, y_std.min(axis=0))
-            score = exact_hvi_device(out["ucb"], front, ref_std)
+            score = _exact_hvi_scores(out, seen_y, prior_mean, prior_variance, reference_point)
             out["acq"].copy_(score)
-        ev_dev = to_device(x_vector[:current_eval], torch.float64, dev)
-        _, idx = gp.select(cand_dev, score, ev_dev, batch_size)
-        x_next = np.array([input_space[i] for i in idx])
-        is_last = current_eval == iterations[-1]
-        if callbacks or is_last:
-            staged = {k: mirror.get(k, tuple(out[k].shape)) for k in keys}
-            for k in keys:
-                staged[k].copy_(out[k], non_blocking=True)
+        _, picked = gp.select(candidates, score, gp.x, batch_size)
+        x_next = np.array([input_space[i] for i in picked])
+        if callbacks or current_eval == starts[-1]:
+            pinned = {k: staging.get(k, tuple(out[k].shape)) for k in out}
+            for k in out:
+                pinned[k].copy_(out[k], non_blocking=True)
             torch.cuda.synchronize()
-            for k in keys:
-                host[k][...] = staged[k].numpy()
-        t3 = time.perf_counter()
+            for k in out:
+                host[k][...] = pinned[k].numpy()
+        clock.tick()
 
-        for b_idx, point in enumerate(x_next):
-            x_vector[current_eval + b_idx] = point
-            y_vector[current_eval + b_idx] = function(point)
+        for offset, point in enumerate(x_next):
+            x_vector[current_eval + offset] = point
+            y_vector[current_eval + offset] = function(point)
         last_eval = current_eval
-        t4 = time.perf_counter()
+        clock.tick()
 
         if callbacks:
-            state = {
-                "iteration": current_eval,
-                "n_evaluations": current_eval + batch_size,
-                "x_vector": x_vector[: current_eval + batch_size],
-                "y_vector": y_vector[: current_eval + batch_size],
-                "mu_objectives": mu_objectives,
-                "variance_objectives": variance_objectives,
-                "acquisition_values": acquisition_values,
-                "x_next": x_next,
-                "hyperparams": optimized_hyperparams.x,
-                "timings": {
-                    "hyperparams": t1 - t0,
-                    "kernels": t2 - t1,
-                    "acquisition": t3 - t2,
-                    "eval": t4 - t3,
-                    "total": t4 - iter_start,
-                },
-            }
-            for callback in callbacks:
-                callback(state)
+            upto = current_eval + batch_size
+            state = {"iteration": current_eval, "n_evaluations": upto, "x_vector": x_vector[:upto],
+                     "y_vector": y_vector[:upto], "mu_objectives": mu_objectives,
+                     "variance_objectives": variance_objectives, "acquisition_values": acquisition_values,
+                     "x_next": x_next, "hyperparams": fitted.x, "timings": clock.timings()}
+            for notify in callbacks:
+                notify(state)
 
     return x_vector, y_vector, last_eval + 1
 
 
 class BayesianOptimization:
-    """Multi-objective Bayesian optimisation; reference bayesian_optimization.py:250-488."""
+    """Multi-objective Bayesian optimisation over an integer Cartesian grid (reference :250-488)."""
 
-    def __init__(self, function: Callable[[np.ndarray], np.ndarray], bounds: List[Tuple[int, int]],
-                 n_objectives: int = 3, n_iterations: int = 10, **kwargs: Any):
-        """Same arguments and kwargs as the reference (:259-332): callbacks, prior_mean, prior_variance,
-        length_scales, betas, batch_size, initial_samples.  Extra opt-in kwarg: ``acquisition``
-        ("sum_ucb" default = reference behaviour, or "exact_hvi")."""
-        self.function = function
-        self.bounds = bounds
-        self.n_objectives = n_objectives
-        self.n_iterations = n_iterations
-
-        callbacks_param = kwargs.get("callbacks", None)
-        if callbacks_param is not None:
-            self.callbacks = callbacks_param if isinstance(callbacks_param, list) else [callbacks_param]
-        else:
-            self.callbacks = []
-
-        self.prior_mean = np.array(kwargs.get("prior_mean", [DEFAULT_PRIOR_MEAN] * n_objectives),
-                                   dtype=NUMBA_FLOAT_TYPE)
-        self.prior_variance = np.array(kwargs.get("prior_variance", [DEFAULT_PRIOR_VARIANCE] * n_objectives),
-                                       dtype=NUMBA_FLOAT_TYPE)
-        self.length_scales = np.array(kwargs.get("length_scales", [DEFAULT_LENGTH_SCALE] * n_objectives),
-                                      dtype=NUMBA_FLOAT_TYPE)
-        self.betas = np.array(kwargs.get("betas", [DEFAULT_BETA] * n_objectives), dtype=NUMBA_FLOAT_TYPE)
-        self.batch_size = kwargs.get("batch_size", DEFAULT_BATCH_SIZE)
-        self.initial_samples = kwargs.get("initial_samples", DEFAULT_INITIAL_SAMPLES)
-        self.acquisition = kwargs.get("acquisition", "sum_ucb")
+    def __init__(self, function, bounds, n_objectives=3, n_iterations=10, **kwargs):
+        """kwargs as in the reference (:277-332): ``callbacks``, ``prior_mean``, ``prior_variance``,
+        ``length_scales``, ``betas``, ``batch_size``, ``initial_samples``; plus the opt-in
+        ``acquisition`` ("sum_ucb" = reference behaviour, "exact_hvi").  ``function`` may be any Python
+        callable (the reference needs an ``@njit`` function)."""
+        self.function, self.bounds = function, bounds
+        self.n_objectives, self.n_iterations = n_objectives, n_iterations
         self.dim = len(bounds)
 
-        # integer Cartesian grid, upper bound exclusive (:338-340)
-        ranges = [np.arange(b[0], b[1]) for b in bounds]
-        mesh = np.meshgrid(*ranges, indexing="ij")
-        self.input_space = np.stack([g.ravel() for g in mesh], axis=-1)
+        cbs = kwargs.get("callbacks")
+        self.callbacks = [] if cbs is None else (cbs if isinstance(cbs, list) else [cbs])
+        per_objective = {"prior_mean": cfg.DEFAULT_PRIOR_MEAN, "prior_variance": cfg.DEFAULT_PRIOR_VARIANCE,
+                         "length_scales": cfg.DEFAULT_LENGTH_SCALE, "betas": cfg.DEFAULT_BETA}
+        for name, default in per_objective.items():
+            setattr(self, name, np.array(kwargs.get(name, [default] * n_objectives), dtype=cfg.NUMBA_FLOAT_TYPE))
+        self.batch_size = kwargs.get("batch_size", cfg.DEFAULT_BATCH_SIZE)
+        self.initial_samples = kwargs.get("initial_samples", cfg.DEFAULT_INITIAL_SAMPLES)
+        self.acquisition = kwargs.get("acquisition", "sum_ucb")
+
+        # candidate set: every integer point of the box, upper bounds exclusive (:338-340)
+        axes = np.meshgrid(*[np.arange(lo, hi) for lo, hi in bounds], indexing="ij")
+        self.input_space = np.stack([a.ravel() for a in axes], axis=-1)
         n_cand = len(self.input_space)
 
         self.total_samples = self.initial_samples + self.n_iterations * self.batch_size
-        self.x_vector = np.zeros((self.total_samples, self.dim), dtype=NUMBA_FLOAT_TYPE)
-        self.y_vector = np.zeros((self.total_samples, n_objectives), dtype=NUMBA_FLOAT_TYPE)
-        self.kernel_matrices = np.zeros((n_objectives, self.total_samples, self.total_samples),
-                                        dtype=NUMBA_FLOAT_TYPE)
-        # the reference preallocates k_star (m, T, M) here (:362-365); the fused path never materialises it
-        self.k_star = None
-        self.mu_objectives = np.zeros((n_objectives, n_cand), dtype=NUMBA_FLOAT_TYPE)
-        self.variance_objectives = np.zeros((n_objectives, n_cand), dtype=NUMBA_FLOAT_TYPE)
-        self.std_mu_objectives = np.zeros((n_objectives, n_cand), dtype=NUMBA_FLOAT_TYPE)
-        self.std_variance_objectives = np.zeros((n_objectives, n_cand), dtype=NUMBA_FLOAT_TYPE)
-        self.ucb = np.zeros((n_objectives, n_cand), dtype=NUMBA_FLOAT_TYPE)
-        self.acquisition_values = np.zeros(n_cand, dtype=NUMBA_FLOAT_TYPE)
+        zeros = lambda *shape: np.zeros(shape, dtype=cfg.NUMBA_FLOAT_TYPE)  # noqa: E731
+        self.x_vector = zeros(self.total_samples, self.dim)
+        self.y_vector = zeros(self.total_samples, n_objectives)
+        self.kernel_matrices = zeros(n_objectives, self.total_samples, self.total_samples)
+        self.k_star = None  # the reference preallocates (m, T, M) here (:362-365); never materialised on the GPU path
+        for name in _HOST_BUFFERS.values():
+            setattr(self, name, zeros(n_cand) if name == "acquisition_values" else zeros(n_objectives, n_cand))
 
-        self.n_evaluations = initialize_lhs_integer(
-            x_vector=self.x_vector, y_vector=self.y_vector, bounds=np.array(self.bounds, dtype=np.int64),
-            function=self.function, n_samples=self.initial_samples)
-
-        if np.all(self.prior_mean == DEFAULT_PRIOR_MEAN):  # exact-equality auto-detection (:413)
+        self.n_evaluations = initialize_lhs_integer(x_vector=self.x_vector, y_vector=self.y_vector,
+                                                    bounds=np.array(bounds, dtype=np.int64), function=function,
+                                                    n_samples=self.initial_samples)
+        # "left at the default" is detected by exact equality, like the reference (:413, :419)
+        if np.all(self.prior_mean == cfg.DEFAULT_PRIOR_MEAN):
             self.prior_mean = compute_prior_mean(self.y_vector, self.n_evaluations, n_objectives)
-        if np.all(self.prior_variance == DEFAULT_PRIOR_VARIANCE):  # (:419)
+        if np.all(self.prior_variance == cfg.DEFAULT_PRIOR_VARIANCE):
             self.prior_variance = compute_prior_variance(self.y_vector, self.n_evaluations, n_objectives)
-
-        self.reference_point = np.array([0.0] * n_objectives)
+        self.reference_point = np.zeros(n_objectives)
 
     def optimize(self) -> None:
-        """Run the optimisation loop (:427-463)."""
+        """Run the loop (reference :427-463)."""
+        buffers = {name: getattr(self, name) for name in
+                   ("x_vector", "y_vector", "kernel_matrices", "k_star", *_HOST_BUFFERS.values(), "input_space",
+                    "prior_mean", "prior_variance", "reference_point", "n_evaluations", "total_samples",
+                    "n_objectives", "function", "betas", "length_scales", "batch_size", "bounds")}
         self.x_vector, self.y_vector, self.n_evaluations = optimize(
-            x_vector=self.x_vector, y_vector=self.y_vector, kernel_matrices=self.kernel_matrices, k_star=self.k_star,
-            mu_objectives=self.mu_objectives, variance_objectives=self.variance_objectives,
-            std_mu_objectives=self.std_mu_objectives, std_variance_objectives=self.std_variance_objectives,
-            ucb=self.ucb, acquisition_values=self.acquisition_values, input_space=self.input_space,
-            prior_mean=self.prior_mean, prior_variance=self.prior_variance, reference_point=self.reference_point,
-            n_evaluations=self.n_evaluations, total_samples=self.total_samples, n_objectives=self.n_objectives,
-            function=self.function, betas=self.betas, length_scales=self.length_scales, batch_size=self.batch_size,
-            bounds=self.bounds, callbacks=self.callbacks if self.callbacks else None, acquisition=self.acquisition)
+            **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition)
 
     def pareto_analysis(self) -> np.ndarray:
-        """Pareto-efficient objective rows among the evaluated points (:465-488)."""
-        evaluated_y = self.y_vector[: self.n_evaluations]
-        evaluated_x = self.x_vector[: self.n_evaluations]
-        pareto_inputs, pareto_objectives = compute_pareto_front(evaluated_x, evaluated_y)
-        print_pareto_analysis(pareto_inputs, pareto_objectives)
-        return pareto_objectives
+        """Pareto-efficient objective rows among the evaluated points (reference :465-488)."""
+        upto = self.n_evaluations
+        inputs, objectives = compute_pareto_front(self.x_vector[:upto], self.y_vector[:upto])
+        print_pareto_analysis(inputs, objectives)
+        return objectives
