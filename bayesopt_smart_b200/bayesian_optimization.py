@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import config as cfg
+from . import distributed as bd
 from .acquisition import exact_hvi_device
 from .engine import DeviceGP, PinnedMirror, require_cuda, to_device
 from .numba_kernels import (compute_prior_mean, compute_prior_variance, initialize_lhs_integer,
@@ -50,6 +51,19 @@ def _exact_hvi_scores(out, y_seen, prior_mean, prior_variance, reference_point):
     return exact_hvi_device(out["ucb"], front, ref_std)
 
 
+def _gather_shards(out, per_rank, n_total):
+    """All-gather the per-candidate arrays of every rank (shards padded to equal length) -> full arrays."""
+    full = {}
+    for k, t in out.items():
+        rows = t.reshape(-1, t.shape[-1])  # (m or 1, shard)
+        pad = torch.zeros((rows.shape[0], per_rank), dtype=t.dtype, device=t.device)
+        pad[:, : rows.shape[1]] = rows
+        g = bd.all_gather_cat(pad.T.contiguous())  # (world * per_rank, rows)
+        g = g[:n_total].T.contiguous()
+        full[k] = g.reshape(-1) if t.dim() == 1 else g
+    return full
+
+
 def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, variance_objectives, std_mu_objectives,
              std_variance_objectives, ucb, acquisition_values, input_space, prior_mean, prior_variance,
              reference_point, n_evaluations, total_samples, n_objectives, function, betas, length_scales,
@@ -64,11 +78,20 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
     untouched (K* is never materialised).  ``acquisition="exact_hvi"`` swaps the reference's sum-UCB score
     for the exact hypervolume improvement (2 or 3 objectives).  Returns ``(x_vector, y_vector,
     last_eval + 1)`` -- the reference's own off-by-batch quirk (:247).
+
+    Multi-GPU: when ``torch.distributed`` is initialised (one process per GPU) every rank calls this with
+    the same arguments; rank r scores candidates ``distributed.shard_range(M, world, r)``, the per-rank
+    top-k lists are all-gathered and merged identically everywhere, so all ranks evaluate the same batch
+    and keep identical ``x_vector`` / ``y_vector``.  Scores do not depend on the sharding, so the trace
+    equals the single-GPU one bit for bit.  The per-candidate host arrays are all-gathered when needed.
     """
     device = require_cuda()
     gp = DeviceGP(device)
-    candidates = to_device(input_space, None, device)  # uploaded once, stays in HBM
+    rank, world = bd.world_info()
+    lo, hi = bd.shard_range(input_space.shape[0], world, rank)
+    candidates = to_device(input_space[lo:hi], None, device)  # this rank's shard, uploaded once, stays in HBM
     n_cand, m = candidates.shape[0], y_vector.shape[1]
+    per_rank = bd.shard_range(input_space.shape[0], world, 0)[1]
     out = {k: torch.empty((n_cand,) if k == "acq" else (m, n_cand), dtype=torch.float64, device=device)
            for k in _HOST_BUFFERS}
     host = dict(mu=mu_objectives, var=variance_objectives, std_mu=std_mu_objectives,
@@ -94,14 +117,22 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
         if acquisition == "exact_hvi":
             score = _exact_hvi_scores(out, seen_y, prior_mean, prior_variance, reference_point)
             out["acq"].copy_(score)
-        _, picked = gp.select(candidates, score, gp.x, batch_size)
+        if world == 1:
+            _, picked = gp.select(candidates, score, gp.x, batch_size)
+        else:
+            # slack = n: even if every listed row of a rank were an evaluated point, enough remain
+            _, top_idx = bd.select_next_batch_sharded(gp, candidates, score, gp.x, batch_size, lo,
+                                                      slack=min(current_eval + 16, 1000))
+            picked = top_idx.cpu().numpy()
+            picked = picked[picked >= 0]
         x_next = np.array([input_space[i] for i in picked])
         if callbacks or current_eval == starts[-1]:
-            pinned = {k: staging.get(k, tuple(out[k].shape)) for k in out}
-            for k in out:
-                pinned[k].copy_(out[k], non_blocking=True)
+            full = out if world == 1 else _gather_shards(out, per_rank, input_space.shape[0])
+            pinned = {k: staging.get(k, tuple(full[k].shape)) for k in full}
+            for k in full:
+                pinned[k].copy_(full[k], non_blocking=True)
             torch.cuda.synchronize()
-            for k in out:
+            for k in full:
                 host[k][...] = pinned[k].numpy()
         clock.tick()
 

@@ -67,10 +67,19 @@ def select_next_batch_sharded(gp, cand_shard: torch.Tensor, acq_shard: torch.Ten
     length ``batch_size`` on the device, identical on every rank.
     """
     n = acq_shard.numel()
-    k = min(n, batch_size + slack)
-    vals, idx = gp.topk(acq_shard, k, index_base)
-    flags = gp.match_rows(idx, cand_shard, evaluated, index_base)
-    vals = torch.where(flags.bool(), torch.full_like(vals, float("-inf")), vals)
+    _, world = world_info(group)
+    k = batch_size + slack  # same list length on every rank (all-gather needs equal sizes)
+    kk = min(n, k)
+    vals, idx = gp.topk(acq_shard, kk, index_base) if kk > 0 else (
+        torch.empty(0, dtype=torch.float64, device=acq_shard.device),
+        torch.empty(0, dtype=torch.int64, device=acq_shard.device))
+    if kk > 0:
+        flags = gp.match_rows(idx, cand_shard, evaluated, index_base)
+        # an evaluated row is dropped from the ranking entirely: index -1 marks "no entry" for the merge
+        idx = torch.where(flags.bool(), torch.full_like(idx, -1), idx)
+    if kk < k:  # short shard: pad the list with empty entries
+        vals = torch.cat([vals, torch.full((k - kk,), float("nan"), dtype=vals.dtype, device=vals.device)])
+        idx = torch.cat([idx, torch.full((k - kk,), -1, dtype=idx.dtype, device=idx.device)])
     gv, gi = gather_topk(vals, idx, group)
     return merge_topk(gp, gv, gi, batch_size)
 

@@ -36,6 +36,8 @@ class _HostMerge:
 
     def topk_merge(self, vals, idx, k):
         v, i = vals.numpy(), idx.numpy()
+        live = i >= 0  # index -1 marks "no entry" (same convention as the CUDA merge kernel)
+        v, i = v[live], i[live]
         key = np.where(np.isnan(v), -np.inf, v)
         order = np.lexsort((i, -key))[:k]
         return torch.from_numpy(v[order].copy()), torch.from_numpy(i[order].copy())
