@@ -6,6 +6,7 @@
 //   mll = -0.5 |L^-1 yt|^2 - sum(log diag L) - 0.5 n log(2 pi)     (:216-232; yt.alpha == |L^-1 yt|^2)
 #include "factor.cuh"
 #include "mll.cuh"
+#include "rbf.cuh"
 
 namespace bo {
 
@@ -111,6 +112,102 @@ __global__ void mll_sum_kernel(double* __restrict__ out, const double* __restric
   out[s] = t;
 }
 
+// ------------------------------------------------------------------------------------------- small n
+// n <= 128: the whole evaluation of one setting (all objectives, in sequence) in ONE CTA -- Gram matrix,
+// Cholesky, forward substitution and the three MLL terms live in shared memory.  This is the shape of the
+// reference's own use (tens of evaluated points, hundreds of sequential Powell evaluations per iteration:
+// numba_kernels.py:305-315), where launch latency, not arithmetic, is the cost.
+constexpr int SMALL_N = 128;
+
+__global__ void __launch_bounds__(256)
+    mll_small_kernel(double* __restrict__ out, const double* __restrict__ x, int ldx, const double* __restrict__ y,
+                     int ldy, int n, int d, int m, ObjParams hp0, const double* __restrict__ ls_all,
+                     const double* __restrict__ jit_all) {
+  extern __shared__ double sm[];
+  double(*A)[SMALL_N + 1] = reinterpret_cast<double(*)[SMALL_N + 1]>(sm);  // Gram / factor (lower)
+  double* xs = sm + SMALL_N * (SMALL_N + 1);                                // n x d coordinates
+  double* yt = xs + SMALL_N * BO_MAX_DIMS;                                  // standardised targets, then z
+  double* scratch = yt + SMALL_N;                                           // 8 doubles
+  __shared__ int nan_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x;
+  const double jit = jit_all[s];
+  if (tid == 0) nan_flag = 0;
+  for (int e = tid; e < n * d; e += 256) xs[e] = x[(long long)(e / d) * ldx + (e % d)];
+  __syncthreads();
+  double total = 0.0;
+  for (int o = 0; o < m; ++o) {
+    const double ls = ls_all[(long long)s * m + o];
+    const double coef = -0.5 / (ls * ls);
+    // ---- standardised targets (population std of y - mu0, skipped when 0: numba_kernels.py:201-208)
+    double acc = 0.0;
+    for (int i = tid; i < n; i += 256) acc += y[(long long)i * ldy + o] - hp0.prior_mean[o];
+    const double mean = block_sum(acc, scratch) / n;
+    acc = 0.0;
+    for (int i = tid; i < n; i += 256) {
+      const double c = (y[(long long)i * ldy + o] - hp0.prior_mean[o]) - mean;
+      acc = fma(c, c, acc);
+    }
+    const double sd = sqrt(block_sum(acc, scratch) / n);
+    for (int i = tid; i < n; i += 256) {
+      double c = y[(long long)i * ldy + o] - hp0.prior_mean[o];
+      if (sd > 0.0) c /= sd;
+      yt[i] = c;
+    }
+    // ---- correlation matrix + jitter, lower triangle
+    for (int e = tid; e < n * n; e += 256) {
+      const int i = e / n, j = e - i * n;
+      if (j > i) continue;
+      double sq = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double diff = xs[i * d + k] - xs[j * d + k];
+        sq = fma(diff, diff, sq);
+      }
+      A[i][j] = rbf_exp(sq * coef, kExp2Tab) + (i == j ? jit : 0.0);
+    }
+    // ---- Cholesky in place, one barrier per column; same pivot policy as potf2_kernel
+    const double neg_tol = 1.4901161193847656e-08 * (1.0 + jit);
+    double logdiag = 0.0;
+    for (int j = 0; j < n; ++j) {
+      __syncthreads();
+      double piv = A[j][j];
+      if (!(piv >= jit)) {
+        if (!(piv > -neg_tol) && tid == 0) nan_flag = 1;
+        piv = fmax(jit, 2.220446049250313e-16);
+      }
+      const double dsq = sqrt(piv);
+      logdiag += log(dsq);  // same value in every thread
+      __syncthreads();      // everybody has read A[j][j] and column j before it is rescaled
+      for (int i = j + tid; i < n; i += 256) A[i][j] = (i == j) ? dsq : A[i][j] / dsq;
+      __syncthreads();
+      const int rem = n - j - 1;
+      for (int e = tid; e < rem * rem; e += 256) {
+        const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+        if (k <= i) A[i][k] = fma(-A[i][j], A[k][j], A[i][k]);
+      }
+    }
+    __syncthreads();
+    // ---- z = L^-1 yt by forward substitution (warp 0; lanes split the dot product)
+    if (warp == 0) {
+      for (int i = 0; i < n; ++i) {
+        double p = 0.0;
+        for (int k = lane; k < i; k += 32) p = fma(A[i][k], yt[k], p);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+        if (lane == 0) yt[i] = (yt[i] - p) / A[i][i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    acc = 0.0;
+    for (int i = tid; i < n; i += 256) acc = fma(yt[i], yt[i], acc);
+    const double fit = block_sum(acc, scratch);
+    total += -0.5 * fit - logdiag - 0.5 * n * log(2.0 * 3.14159265358979323846);
+    __syncthreads();
+  }
+  if (tid == 0) out[s] = nan_flag ? __longlong_as_double(0x7ff8000000000000ll) : total;
+}
+
 }  // namespace
 
 static int group_settings(int npad, int m, int n_settings) {
@@ -146,6 +243,26 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
   const int npad = round_up(n, TM);
   const int gs = group_settings(npad, m, n_settings);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
+  if (n <= SMALL_N) {
+    // one CTA per setting; hyper-parameters travel through the head of the workspace
+    double* ls_dev = reinterpret_cast<double*>(ws);
+    double* jit_small = ls_dev + (size_t)n_settings * m;
+    BO_CUDA(cudaMemcpyAsync(ls_dev, length_scales, sizeof(double) * n_settings * m, cudaMemcpyHostToDevice, stream));
+    BO_CUDA(cudaMemcpyAsync(jit_small, jitter, sizeof(double) * n_settings, cudaMemcpyHostToDevice, stream));
+    ObjParams hps;
+    memset(&hps, 0, sizeof(hps));
+    for (int o = 0; o < m; ++o) hps.prior_mean[o] = prior_mean[o];
+    const size_t smem = (size_t)(SMALL_N * (SMALL_N + 1) + SMALL_N * BO_MAX_DIMS + SMALL_N + 8) * sizeof(double);
+    static bool small_attr = false;
+    if (!small_attr) {
+      BO_CUDA(cudaFuncSetAttribute(mll_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      small_attr = true;
+    }
+    mll_small_kernel<<<n_settings, 256, smem, stream>>>(out, x, ldx, y, ldy, n, d, m, hps, ls_dev, jit_small);
+    BO_LAUNCH_CHECK("mll_small_kernel");
+    BO_CUDA(cudaStreamSynchronize(stream));
+    return BO_OK;
+  }
   size_t off = 0;
   double* A = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * npad * sizeof(double));
   double* D = reinterpret_cast<double*>(ws + off);    off += align256((size_t)gs * m * npad * 64 * sizeof(double));

@@ -124,18 +124,32 @@ def optimize_hyperparams_mll(x_vector, y_vector, kernel_matrix, prior_mean, prio
     bayesian_optimization.py:129).
     """
     dev = require_cuda()
+    lib = _lib.load()
     n_objectives = y_vector.shape[1]
-    x_dev = to_device(x_vector[:current_eval], _F64, dev)
-    y_dev = to_device(y_vector[:current_eval], _F64, dev)
+    n = int(current_eval)
+    x_dev = to_device(x_vector[:n], _F64, dev)
+    y_dev = to_device(y_vector[:n], _F64, dev)
     initial_guess = np.concatenate([length_scales, prior_variance])
     bounds = [(HYPERPARAM_MIN_BOUND, None)] * (2 * n_objectives)
 
+    # everything the objective needs is prepared once: Powell calls it hundreds of times per iteration
+    ws_bytes = lib.bo_mll_workspace_bytes(n, n_objectives, 1)
+    ws = _ws.get("mll", ws_bytes, dev)
+    result = torch.empty(1, dtype=_F64).pin_memory()  # the kernel writes the value straight into host memory
+    ls_host = np.zeros(n_objectives, dtype=np.float64)
+    jit_host = np.array([CHOLESKY_JITTER], dtype=np.float64)
+    mean_keep, pm = _lib.host_doubles(prior_mean, n_objectives)
+    args = (result.data_ptr(), x_dev.data_ptr(), x_dev.stride(0), y_dev.data_ptr(), y_dev.stride(0), n,
+            x_dev.shape[1], n_objectives, pm, ls_host.ctypes.data_as(_lib._dp), jit_host.ctypes.data_as(_lib._dp), 1,
+            ws.data_ptr(), ws_bytes, _stream())
+
     def objective(params):
-        ls = np.asarray(params[:n_objectives], dtype=np.float64)
-        val = mll_batched(x_dev, y_dev, prior_mean, ls[None, :], [CHOLESKY_JITTER], current_eval)[0]
-        if np.isnan(val):
+        ls_host[:] = params[:n_objectives]
+        _lib.check(lib.bo_mll_batched_f64(*args))  # synchronising call
+        val = float(result[0])
+        if val != val:
             raise np.linalg.LinAlgError("Matrix is not positive definite")
-        return -float(val)
+        return -val
 
     optim_result = minimize(objective, initial_guess, method=HYPERPARAM_METHOD, bounds=bounds,
                             options={"xtol": HYPERPARAM_XTOL, "ftol": HYPERPARAM_FTOL,
