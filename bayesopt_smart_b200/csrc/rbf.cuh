@@ -5,7 +5,7 @@
 //   n = rint(x * 64/ln2),  r = x - n*ln2/64 (two-term Cody-Waite, |r| <= ln2/128),
 //   exp(x) = 2^(n>>6) * T[n & 63] * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120),   T[j] = 2^(j/64)
 // Truncation error r^6/720 < 3.6e-17; total error ~1 ulp (the reference's own exp runs under fastmath).
-// Domain: x <= 0 (x = -0.5 * sq / ls^2).  Results below 2^-1020 are flushed to zero.
+// Domain: x <= 0 (x = -0.5 * sq / ls^2).  Results below exp(-706) are flushed to zero.
 #pragma once
 
 namespace bo {
@@ -30,27 +30,31 @@ static __device__ const double kExp2Tab[64] = {
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951,
 };
 
+// Coefficients live in the constant bank so that DFMA takes them as direct c[][] operands; as literals the
+// compiler rebuilt each 64-bit constant with two UMOVs per use (17 % of the K* kernel's issue slots).
+//   [0] 64/ln2   [1] -ln2/64 high part (low 32 mantissa bits zero: n*hi exact)   [2] -(ln2/64 - hi)
+//   [3] 1/120    [4] 1/24    [5] 1/6
+static __device__ __constant__ double kExpCoef[6] = {
+    92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12,
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
 // tab: 64 doubles 2^(j/64), in shared memory (hot kernel) or kExp2Tab itself (L1-cached global)
 __device__ __forceinline__ double rbf_exp(double x, const double* __restrict__ tab) {
-  const double kInv = 92.33248261689366;   // 64 / ln 2
-  const double kHi = 0.01083042469326756;     // ln2/64, top 32 mantissa bits (n * kHi is exact)
-  const double kLo = 2.9815858269852933e-12;   // ln2/64 - kHi
-  const double kMagic = 6755399441055744.0;      // 1.5 * 2^52: adds round-to-nearest-integer
-  if (!(x > -708.0)) return 0.0;                  // exp(x) < 1e-307 (also keeps n inside int range)
-  const double t = fma(x, kInv, kMagic);
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
+  const double xc = fmax(x, -706.0);         // keeps n inside int range and the result normal
+  const double t = fma(xc, kExpCoef[0], kMagic);
   const int n = __double2loint(t);
   const double nd = t - kMagic;
-  double r = fma(nd, -kHi, x);
-  r = fma(nd, -kLo, r);
-  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
+  double r = fma(nd, kExpCoef[1], xc);
+  r = fma(nd, kExpCoef[2], r);
+  double p = fma(r, kExpCoef[3], kExpCoef[4]);
+  p = fma(p, r, kExpCoef[5]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double v = tab[n & 63] * p;
-  const int e = n >> 6;
-  const double scaled = __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
-  return (e < -1020) ? 0.0 : scaled;
+  const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+  return (x < -706.0) ? 0.0 : scaled;  // exp(x) < 2.5e-307 is flushed to zero (also maps NaN-free inputs only)
 }
 
 }  // namespace bo

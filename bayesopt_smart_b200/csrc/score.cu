@@ -32,6 +32,8 @@ namespace {
 // Rows >= n need no masking: the packed W has zero rows/columns there, and alpha is zero.
 constexpr int KS_ROWS = 256;
 
+// 4 CTAs/SM (<= 128 registers); 6 CTAs/SM was measured and is not faster: the kernel is bound by its
+// write stream (8*m*npad bytes per candidate), see DESIGN.md.
 template <typename CT, int D, int MOBJ>
 __global__ void __launch_bounds__(128, 4)
     kstar_pack_kernel(double* __restrict__ Kp, double* __restrict__ meandot, const CT* __restrict__ cand, int ldc,

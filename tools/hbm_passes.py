@@ -49,6 +49,18 @@ def main():
     lib = _lib.load()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     gp = DeviceGP()
+    big = torch.empty(2 << 30, dtype=torch.uint8, device="cuda").view(torch.float64)
+    t = timed(lambda: big.fill_(1.0), flush)
+    emit(kind="write_only_fill_2GiB", bytes=big.numel() * 8, seconds=t, gbs=big.numel() * 8 / t / 1e9, peak_gbs=PEAK,
+         frac=big.numel() * 8 / t / 1e9 / PEAK)
+    src = torch.empty_like(big)
+    t = timed(lambda: big.copy_(src), flush)
+    emit(kind="copy_2GiB_read_plus_write", bytes=2 * big.numel() * 8, seconds=t, gbs=2 * big.numel() * 8 / t / 1e9,
+         peak_gbs=PEAK, frac=2 * big.numel() * 8 / t / 1e9 / PEAK)
+    t = timed(lambda: big.sum(), flush)
+    emit(kind="read_only_sum_2GiB", bytes=big.numel() * 8, seconds=t, gbs=big.numel() * 8 / t / 1e9, peak_gbs=PEAK,
+         frac=big.numel() * 8 / t / 1e9 / PEAK)
+    del big, src
     for m, M in [(2, 16_000_000), (3, 8_000_000)]:
         mu = torch.randn(m, M, dtype=torch.float64, device="cuda")
         var = torch.rand(m, M, dtype=torch.float64, device="cuda")
