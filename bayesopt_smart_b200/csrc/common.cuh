@@ -42,7 +42,6 @@ struct ObjParams {
   double prior_var[BO_MAX_OBJECTIVES];
   double neg_half_inv_ls2[BO_MAX_OBJECTIVES];  // -0.5 / ls^2
   double beta[BO_MAX_OBJECTIVES];
-  double inv_sqrt_var[BO_MAX_OBJECTIVES];      // unused by the parity path (division kept), for HVI scaling
 };
 
 int device_sm_count();
@@ -120,11 +119,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 __device__ __forceinline__ double2 lds128(const double* p) { return *reinterpret_cast<const double2*>(p); }
-
-template <typename T>
-__device__ __forceinline__ double cand_to_f64(T v) {
-  return (double)v;
-}
 
 // order-preserving key: larger double -> larger uint64; NaN -> 0 (sorts last); -0.0 == +0.0
 __device__ __forceinline__ unsigned long long order_key(double v) {

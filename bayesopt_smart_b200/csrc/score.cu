@@ -6,9 +6,9 @@
 //   1. kstar_pack_kernel   RBF cross kernel written ONCE as 16 KB tiles in DMMA B-fragment order (so K* is
 //                          generated with N exps per candidate-objective, not N * N/256), fused with the
 //                          posterior-mean dot product k*.alpha (warp-shuffle reduction).
-//   2. trmm_sumsq_kernel   V = W K* on FP64 tensor cores (DMMA.8x8x4), W tiles and K* tiles streamed by
-//                          cp.async.bulk (UBLKCP) through a 4-stage mbarrier ring; V never leaves registers:
-//                          the epilogue reduces sum_i V[i,c]^2 per 128-row block with warp shuffles.
+//   2. trmm_sumsq_kernel   V = W K* on FP64 tensor cores (DMMA.8x8x4), persistent (one CTA per SM), W tiles and
+//                          K* tiles streamed by cp.async.bulk (UBLKCP) through a 4-stage mbarrier ring; V never
+//                          leaves registers: the epilogue reduces sum_i V[i,c]^2 per 128-row block with shuffles.
 //   3. finalize_kernel     var = max(var0 - sum, min_var), mu, standardise, UCB, acq; coalesced writes.
 // All reductions have a fixed order, so a candidate's result does not depend on the chunking or on how the
 // candidate set is sharded across GPUs (bit-identical top-k for any rank count).
@@ -134,9 +134,14 @@ constexpr size_t TR_SMEM = (size_t)TR_STAGES * 2 * TILE_DOUBLES * sizeof(double)
                            + 2 * 2 * TN * sizeof(double)                           // epilogue exchange
                            + 2 * TR_STAGES * sizeof(uint64_t);
 
+// Persistent: the grid is one CTA per SM; CTA b walks work units b, b + gridDim.x, ...  A unit is
+// (objective o, row-block pair pr, candidate tile c) with the candidate tile fastest, so the CTAs resident at
+// any time stream the same W tiles (L2 hits).  The producer lane runs ahead across unit boundaries: the tiles
+// of the next unit are already landing while the consumers reduce the current one.
 __global__ void __launch_bounds__(TR_THREADS, 1)
     trmm_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const double* __restrict__ Wp,
-                      long long strideWp, const double* __restrict__ Kp, int nb, int chunk_tiles, int live_tiles) {
+                      long long strideWp, const double* __restrict__ Kp, int nb, int chunk_tiles, int live_tiles,
+                      int total_units) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + TR_STAGES * TILE_DOUBLES;
@@ -146,14 +151,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = (nb + 1) / 2;
-  const int u = blockIdx.x;
-  // grid decode uses the live tile count of this chunk; the K* / part layouts use chunk_tiles
-  const int c = u % live_tiles;
-  const int pr = (u / live_tiles) % npairs;
-  const int o = u / (live_tiles * npairs);
   const int nkt_total = nb * KT_PER_BLOCK;
-  const int ib_first = nb - 1 - pr;  // heavy block first, its light partner second: nb + 1 k-blocks per CTA
-  const int n_rb = (pr == ib_first) ? 1 : 2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TR_STAGES; ++s) {
@@ -164,28 +162,35 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
   }
   __syncthreads();
 
-  const double* Wo = Wp + (long long)o * strideWp;
-  const double* Bo = Kp + ((long long)o * chunk_tiles + c) * nkt_total * TILE_DOUBLES;
-
   if (warp == TR_CONSUMER_WARPS) {
     // ===== producer: one lane streams tiles with the bulk-copy engine =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int rb = 0; rb < n_rb; ++rb) {
-        const int ib = rb == 0 ? ib_first : pr;
-        const int nkt = (ib + 1) * KT_PER_BLOCK;
-        const double* At = Wo + wpack_tile_offset(ib) * TILE_DOUBLES;
-        for (int kt = 0; kt < nkt; ++kt) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], 2 * TILE_DOUBLES * sizeof(double));
-          bulk_g2s(sA + stage * TILE_DOUBLES, At + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
-                   &full[stage]);
-          bulk_g2s(sB + stage * TILE_DOUBLES, Bo + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
-                   &full[stage]);
-          if (++stage == TR_STAGES) {
-            stage = 0;
-            phase ^= 1;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        // grid decode uses the live tile count of this chunk; the K* / part layouts use chunk_tiles
+        const int c = u % live_tiles;
+        const int pr = (u / live_tiles) % npairs;
+        const int o = u / (live_tiles * npairs);
+        const int ib_first = nb - 1 - pr;  // heavy block first, its light partner second: nb + 1 k-blocks
+        const int n_rb = (pr == ib_first) ? 1 : 2;
+        const double* Wo = Wp + (long long)o * strideWp;
+        const double* Bo = Kp + ((long long)o * chunk_tiles + c) * nkt_total * TILE_DOUBLES;
+        for (int rb = 0; rb < n_rb; ++rb) {
+          const int ib = rb == 0 ? ib_first : pr;
+          const int nkt = (ib + 1) * KT_PER_BLOCK;
+          const double* At = Wo + wpack_tile_offset(ib) * TILE_DOUBLES;
+          for (int kt = 0; kt < nkt; ++kt) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], 2 * TILE_DOUBLES * sizeof(double));
+            bulk_g2s(sA + stage * TILE_DOUBLES, At + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
+                     &full[stage]);
+            bulk_g2s(sB + stage * TILE_DOUBLES, Bo + (long long)kt * TILE_DOUBLES, TILE_DOUBLES * sizeof(double),
+                     &full[stage]);
+            if (++stage == TR_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -198,48 +203,39 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
   const int g = lane >> 2, t = lane & 3;
   int stage = 0;
   uint32_t phase = 0;
-  for (int rb = 0; rb < n_rb; ++rb) {
-    const int ib = rb == 0 ? ib_first : pr;
-    const int nkt = (ib + 1) * KT_PER_BLOCK;
-    // Inside the diagonal 128x128 block W is lower triangular: for this warp's rows (wm*64 + 8i + g) the
-    // k-tile kd (16 wide, counted from the start of the diagonal block) only meets non-zeros for row
-    // atoms i >= 2*(kd - 4*wm); tiles with kd - 4*wm >= 4 are skipped entirely.
-    const int kt_diag = ib * KT_PER_BLOCK;
-    double acc[8][4][2];
+  int epi = 0;  // epilogue counter: alternates the exchange buffer
+  for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    const int c = u % live_tiles;
+    const int pr = (u / live_tiles) % npairs;
+    const int o = u / (live_tiles * npairs);
+    const int ib_first = nb - 1 - pr;
+    const int n_rb = (pr == ib_first) ? 1 : 2;
+    for (int rb = 0; rb < n_rb; ++rb, ++epi) {
+      const int ib = rb == 0 ? ib_first : pr;
+      const int nkt = (ib + 1) * KT_PER_BLOCK;
+      // Inside the diagonal 128x128 block W is lower triangular: for this warp's rows (wm*64 + 8i + g) the
+      // k-tile kd (16 wide, counted from the start of the diagonal block) only meets non-zeros for row
+      // atoms i >= 2*(kd - 4*wm); tiles with kd - 4*wm >= 4 are skipped entirely.
+      const int kt_diag = ib * KT_PER_BLOCK;
+      double acc[8][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = 0; kt < nkt; ++kt) {
-      mbar_wait(&full[stage], phase);
-      const double* a_base = sA + stage * TILE_DOUBLES + wm * 1024 + lane * 2;
-      const double* b_base = sB + stage * TILE_DOUBLES + wn * 512 + lane * 2;
-      const int i_min = 2 * (kt - kt_diag - 4 * wm);  // <= 0: every row atom is live
-      if (i_min <= 0) {
+      for (int kt = 0; kt < nkt; ++kt) {
+        mbar_wait(&full[stage], phase);
+        const double* a_base = sA + stage * TILE_DOUBLES + wm * 1024 + lane * 2;
+        const double* b_base = sB + stage * TILE_DOUBLES + wn * 512 + lane * 2;
+        const int i_min = 2 * (kt - kt_diag - 4 * wm);  // <= 0: every row atom is live
+        if (i_min <= 0) {
 #pragma unroll
-        for (int sp = 0; sp < 2; ++sp) {
-          double2 b[4];
+          for (int sp = 0; sp < 2; ++sp) {
+            double2 b[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
+            for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const double2 a = lds128(a_base + (i * 2 + sp) * 64);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
-          }
-        }
-      } else if (i_min < 8) {
-#pragma unroll
-        for (int sp = 0; sp < 2; ++sp) {
-          double2 b[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
-#pragma unroll
-          for (int i = 2; i < 8; ++i) {
-            if (i >= i_min) {  // warp-uniform
+            for (int i = 0; i < 8; ++i) {
               const double2 a = lds128(a_base + (i * 2 + sp) * 64);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
@@ -247,35 +243,54 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
               for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
             }
           }
+        } else if (i_min < 8) {
+#pragma unroll
+          for (int sp = 0; sp < 2; ++sp) {
+            double2 b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = lds128(b_base + (j * 2 + sp) * 64);
+#pragma unroll
+            for (int i = 2; i < 8; ++i) {
+              if (i >= i_min) {  // warp-uniform
+                const double2 a = lds128(a_base + (i * 2 + sp) * 64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == TR_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
-      if (++stage == TR_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
-    }
 
-    // epilogue: sum over this warp's 64 rows of V^2, per candidate column
-    double* rbuf = red + rb * 2 * TN;
+      // epilogue: sum over this warp's 64 rows of V^2, per candidate column
+      double* rbuf = red + (epi & 1) * 2 * TN;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        double s = 0.0;
+        for (int r = 0; r < 2; ++r) {
+          double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fma(acc[i][j][r], acc[i][j][r], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if (g == 0) rbuf[wm * TN + wn * 32 + j * 8 + 2 * t + r] = s;
+          for (int i = 0; i < 8; ++i) s = fma(acc[i][j][r], acc[i][j][r], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          if (g == 0) rbuf[wm * TN + wn * 32 + j * 8 + 2 * t + r] = s;
+        }
       }
+      // consumer warps only.  The exchange buffer alternates, and a thread can only reach the barrier of
+      // epilogue e+1 after its reads of epilogue e, so buffer e&1 is free again when epilogue e+2 writes it.
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < TN)
+        part[((long long)o * nb + ib) * ld_chunk + (long long)c * TN + threadIdx.x] =
+            rbuf[threadIdx.x] + rbuf[TN + threadIdx.x];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // consumer warps only
-    if (threadIdx.x < TN)
-      part[((long long)o * nb + ib) * ld_chunk + (long long)c * TN + threadIdx.x] =
-          rbuf[threadIdx.x] + rbuf[TN + threadIdx.x];
   }
 }
 
@@ -356,12 +371,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <typename CT, int DMAX>
+template <typename CT, int D>
 int launch_kstar_m(int m, dim3 grid, cudaStream_t st, double* Kp, double* meandot, const CT* cand, int ldc,
                    long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x, int ldx,
                    int n, int npad, int d, const double* alpha, const ObjParams& hp) {
 #define BO_KS(MO)                                                                                              \
-  kstar_pack_kernel<CT, DMAX, MO><<<grid, 128, 0, st>>>(Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles,    \
+  kstar_pack_kernel<CT, D, MO><<<grid, 128, 0, st>>>   (Kp, meandot, cand, ldc, cand0, n_cand, chunk_tiles,    \
                                                         ld_chunk, x, ldx, n, npad, d, alpha, hp)
   switch (m) {
     case 1: BO_KS(1); break;
@@ -536,11 +551,12 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     }
     if (ov) BO_CUDA(cudaStreamWaitEvent(stream, ov->kstar_done[b], 0));
     // grid: candidate tile fastest so that concurrently resident CTAs stream the same W tiles (L2 hits)
-    const unsigned grid = (unsigned)(m * npairs) * (unsigned)tiles;
+    const int units = m * npairs * tiles;
+    const unsigned grid = (unsigned)(units < device_sm_count() ? units : device_sm_count());
     const bool prof = profile_enabled();
     if (prof) profile_begin(stream);
     trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp[b], p.nb,
-                                                             p.chunk_tiles, tiles);
+                                                             p.chunk_tiles, tiles, units);
     // algorithmic work of this launch: m * N^2 flops per live candidate
     if (prof) {
       const long long live = (remaining < p.ld_chunk ? remaining : p.ld_chunk);
