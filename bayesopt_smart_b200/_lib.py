@@ -44,6 +44,17 @@ _SIGNATURES = {
     "bo_score_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                              c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, _dp, _dp,
                              _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
+    "bo_i8_wq_bytes": (c_size_t, [c_int]),
+    "bo_i8_wscale_doubles": (c_size_t, [c_int, c_int]),
+    "bo_i8_quantize_w": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "bo_score_i8_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
+    "bo_score_i8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
+                            c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                            _dp, _dp, _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
+    "bo_i8_kstar_digits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_void_p, _dp, _dp, c_void_p]),
+    "bo_i8_sumsq": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, _dp,
+                            c_void_p]),
     "bo_acquisition_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                    c_longlong, c_int, _dp, _dp, _dp, c_void_p]),
     "bo_topk_workspace_bytes": (c_size_t, [c_longlong, c_int]),

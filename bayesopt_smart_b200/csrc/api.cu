@@ -9,6 +9,7 @@
 #include "factor.cuh"
 #include "gemm.cuh"
 #include "mll.cuh"
+#include "ozaki.cuh"
 #include "score.cuh"
 #include "select.cuh"
 
@@ -321,6 +322,68 @@ int bo_score_f64(double* mu_dev, double* var_dev, double* std_mu_dev, double* st
   out.ucb = ucb_dev; out.acq = acq_dev; out.ld = ld_out;
   return score_candidates(out, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, m, wpack_dev, alpha_dev, hp,
                           min_variance, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t bo_i8_wq_bytes(int n) { return oz_wq_bytes(n); }
+size_t bo_i8_wscale_doubles(int n, int m) { return (size_t)2 * m * round_up(n, OZ_TM); }
+
+int bo_i8_quantize_w(uint8_t* wq_dev, double* wscale_dev, const double* wpack_dev, int n, int m, void* stream) {
+  BO_REQUIRE(wq_dev && wscale_dev && wpack_dev, "null pointer");
+  BO_REQUIRE(n >= 1 && n <= OZ_MAX_N && m >= 1 && m <= BO_MAX_OBJECTIVES, "bad sizes (int8 engine: n <= 16384)");
+  return oz_quantize_w(wq_dev, wscale_dev, wpack_dev, n, m, (cudaStream_t)stream);
+}
+
+size_t bo_score_i8_workspace_bytes(int n, int m, long long n_cand) {
+  return oz_workspace_bytes(make_oz_plan(n, m, n_cand));
+}
+
+int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev, double* ucb_dev,
+                double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
+                const double* x_dev, int ldx, int n, int d, int m, const uint8_t* wq_dev, const double* wscale_dev,
+                const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
+                const double* length_scales_host, const double* betas_host, double min_variance,
+                void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(cand_dev && x_dev && wq_dev && wscale_dev && alpha_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host && betas_host,
+             "null hyper-parameter pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(n >= 1 && d >= 1 && d <= BO_MAX_DIMS && ldc >= d && ld_out >= n_cand, "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, betas_host);
+  if (rc) return rc;
+  ScoreOutputs out;
+  out.mu = mu_dev; out.var = var_dev; out.std_mu = std_mu_dev; out.std_var = std_var_dev;
+  out.ucb = ucb_dev; out.acq = acq_dev; out.ld = ld_out;
+  return oz_score_candidates(out, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, m, wq_dev, wscale_dev,
+                             alpha_dev, hp, min_variance, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bo_i8_kstar_digits(uint8_t* kq_dev, double* meandot_dev, const void* cand_dev, int cand_kind, int ldc,
+                       long long n_cand, const double* x_dev, int ldx, int n, int d, int m,
+                       const double* alpha_dev, const double* prior_variance_host,
+                       const double* length_scales_host, void* stream) {
+  BO_REQUIRE(kq_dev && meandot_dev && cand_dev && x_dev && alpha_dev, "null pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(n >= 1 && n_cand >= 1 && d >= 1 && d <= BO_MAX_DIMS && ldc >= d, "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, nullptr, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN);
+  return oz_kstar_digits(kq_dev, meandot_dev, cand_dev, cand_kind, ldc, 0, n_cand, tiles, tiles, x_dev, ldx, n, d, m,
+                         alpha_dev, hp, (cudaStream_t)stream);
+}
+
+int bo_i8_sumsq(double* q_dev, const uint8_t* wq_dev, const double* wscale_dev, const uint8_t* kq_dev, int n, int m,
+                long long n_cand, int nsplit, const double* prior_variance_host, void* stream) {
+  BO_REQUIRE(q_dev && wq_dev && wscale_dev && kq_dev, "null pointer");
+  BO_REQUIRE(n >= 1 && n <= OZ_MAX_N && n_cand >= 1 && nsplit >= 1 && nsplit <= round_up(n, OZ_TM) / OZ_TM,
+             "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, nullptr, prior_variance_host, nullptr, nullptr);
+  if (rc) return rc;
+  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN);
+  return oz_sumsq(q_dev, (long long)tiles * OZ_TN, wq_dev, wscale_dev, kq_dev, n, m, tiles, tiles, nsplit, hp,
+                  (cudaStream_t)stream);
 }
 
 int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* acq_dev,

@@ -1,0 +1,662 @@
+// ozaki.cu -- INT8 tensor-core engine for the posterior variance: sum_i (W k*)_i^2 by error-free splitting.
+// Reference semantics: update_variance (numba_kernels.py:491-535) -- same quantity as score.cu's DMMA path,
+// computed on tcgen05.mma.kind::i8 instead of DMMA.
+//
+// Number format.  Row i of W is scaled by 2^-e_i (|w| 2^-e_i <= 126/128) and rounded to a 48-bit integer
+// q = rint(w 2^(47-e_i)); a K* entry kt = exp(..) in [0,1] becomes q = rint(kt 2^46).  q is written in BALANCED
+// base-256 digits q = sum_s d_s 256^(5-s), d_s in [-128,127] (top digit of W in [-127,127], of K* in [0,65]):
+// adding 0x80 to each of the five low bytes turns the balanced digits into the plain bytes of the sum, so the
+// digits are the bytes of (q + 0x8080808080) with the low five XORed by 0x80.  With balanced digits the dropped
+// pairs (s + t >= 6) are zero-mean, which is worth two digits of accuracy over unsigned slices.
+//   V_i = pvar 2^(e_i-13) sum_{g=0..5} 256^-g acc_g,   acc_g = sum_{s+t=g} sum_k dW_s[i,k] dK_t[k,c]   (exact int32)
+//       = pvar 2^(e_i-21) (b_0 + 2^-16 b_1 + 2^-32 b_2),  b_j = 256 acc_2j + acc_2j+1             (exact int64)
+//
+// Layout.  Both operands are stored in HBM exactly as the UMMA canonical K-major / no-swizzle shared-memory
+// image of one k-step (32 k), all six planes of a (row block | candidate tile) contiguous:
+//   [plane][row group of 8][k half of 16][row in group][16 bytes]
+// so one cp.async.bulk per operand per k-step fills a pipeline stage, and the smem descriptor is
+// (start, LBO = 128 B between the two k halves, SBO = 256 B between row groups).
+//
+// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warp 1: TMEM allocator + single-thread
+// MMA issuer (21 MMAs 128x80x32 per k-step into 6 TMEM accumulators = 480 columns); warps 2-5: epilogue
+// (tcgen05.ld, pairwise integer recombination a_2j*256 + a_2j+1, three exact int64 -> FP64 conversions, row
+// scale, square, running per-thread sums over all row blocks of the work unit; one transposed shuffle
+// reduction per unit).
+#include "ozaki.cuh"
+
+#include <stdlib.h>
+
+#include "rbf.cuh"
+
+namespace bo {
+
+namespace {
+
+constexpr int OZ_STAGES = 5;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 39936
+constexpr int OZ_TMEM_COLS = 512;
+constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_TN * sizeof(double) +
+                           (2 * OZ_STAGES + 2) * sizeof(uint64_t) + 16;
+
+constexpr unsigned long long OZ_BIAS = 0x0000008080808080ull;  // 0x80 in each of the five low digit bytes
+constexpr double OZ_MAGIC = 6755399441055744.0;                // 1.5 * 2^52
+
+// bytes 0..5 of the result are the balanced digits (least significant first) of rint(v * scale)
+__device__ __forceinline__ unsigned long long balanced_digits(double v, double scale) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(v, scale, OZ_MAGIC));
+  return (bits + OZ_BIAS) ^ OZ_BIAS;
+}
+
+// gather byte `BI` (0..5) of 16 digit words into one 16-byte row (byte b <-> word b)
+template <int BI>
+__device__ __forceinline__ uint4 plane_row(const unsigned long long (&w)[16]) {
+  uint32_t out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      v[e] = BI < 4 ? (uint32_t)w[4 * q + e] : (uint32_t)(w[4 * q + e] >> 32);
+    constexpr int j = BI & 3;
+    const uint32_t t01 = __byte_perm(v[0], v[1], j | ((4 + j) << 4));
+    const uint32_t t23 = __byte_perm(v[2], v[3], j | ((4 + j) << 4));
+    out[q] = __byte_perm(t01, t23, 0x5410);
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// ------------------------------------------------------------------------------------------- W digits
+// element (r, k) of the DMMA-packed W (common.cuh / factor.cu pack_w)
+__device__ __forceinline__ long long wpack_index(int r, int k) {
+  const int ib = r >> 7, rr = r & 127, kt = k >> 4, kk = k & 15;
+  const int wm = rr >> 6, i = (rr >> 3) & 7, g = rr & 7;
+  const int sp = kk >> 3, q = (kk >> 2) & 1, t = kk & 3;
+  return (wpack_tile_offset(ib) + kt) * TILE_DOUBLES + (((wm * 8 + i) * 2 + sp) * 32 + (4 * g + t)) * 2 + q;
+}
+
+// one warp per (objective, row): e_i with max|w| * 128/126 <= 2^e_i
+__global__ void oz_rowscale_kernel(double* __restrict__ wscale, double* __restrict__ qscale,
+                                   const double* __restrict__ wpack, long long strideWp, int n, int npad) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int o = blockIdx.y, lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  double mx = 0.0;
+  if (row < n) {
+    const double* W = wpack + (long long)o * strideWp;
+    for (int k = lane; k <= row; k += 32) mx = fmax(mx, fabs(W[wpack_index(row, k)]));
+  }
+#pragma unroll
+  for (int s = 16; s; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  if (lane == 0) {
+    double ws = 0.0, qs = 0.0;
+    if (mx > 0.0 && mx < 1e300) {
+      int e;
+      frexp(mx * (128.0 / 126.0), &e);  // value = f 2^e, f in [0.5, 1)  =>  value <= 2^e
+      ws = ldexp(1.0, e - 21);  // 2^(e-13) for sum_g 256^-g acc_g, times 2^-8 for the pairwise recombination
+      qs = ldexp(1.0, 47 - e);
+    }
+    wscale[(long long)o * npad + row] = ws;
+    qscale[(long long)o * npad + row] = qs;
+  }
+}
+
+// one thread per 16-byte row of one k-step block: (o, ib, ks, rg, kc, r) -> six plane rows
+__global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long strideWq,
+                                  const double* __restrict__ qscale, const double* __restrict__ wpack,
+                                  long long strideWp, int n, int npad, int nb) {
+  const long long blocks = 2LL * nb * (nb + 1);  // k-step blocks per objective
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y;
+  if (tid >= blocks * 256) return;
+  const long long blk = tid >> 8;
+  const int within = (int)(tid & 255);
+  const int rg = within >> 4, kc = (within >> 3) & 1, r = within & 7;
+  // blk = 2 ib (ib + 1) + ks
+  int ib = (int)((sqrt(1.0 + 2.0 * (double)blk) - 1.0) * 0.5);
+  while (2LL * ib * (ib + 1) > blk) --ib;
+  while (2LL * (ib + 1) * (ib + 2) <= blk) ++ib;
+  const int ks = (int)(blk - 2LL * ib * (ib + 1));
+  const int row = ib * OZ_TM + rg * 8 + r;
+  const int k0 = ks * OZ_KS + kc * 16;
+  const double* W = wpack + (long long)o * strideWp;
+  const double qs = qscale[(long long)o * npad + row];
+  unsigned long long dg[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int k = k0 + b;
+    const double w = (row < n && k <= row) ? W[wpack_index(row, k)] : 0.0;
+    dg[b] = balanced_digits(w, qs);
+  }
+  unsigned char* dst = wq + (long long)o * strideWq + blk * OZ_A_STAGE + rg * 256 + kc * 128 + r * 16;
+  *reinterpret_cast<uint4*>(dst + 0 * OZ_A_PLANE) = plane_row<5>(dg);
+  *reinterpret_cast<uint4*>(dst + 1 * OZ_A_PLANE) = plane_row<4>(dg);
+  *reinterpret_cast<uint4*>(dst + 2 * OZ_A_PLANE) = plane_row<3>(dg);
+  *reinterpret_cast<uint4*>(dst + 3 * OZ_A_PLANE) = plane_row<2>(dg);
+  *reinterpret_cast<uint4*>(dst + 4 * OZ_A_PLANE) = plane_row<1>(dg);
+  *reinterpret_cast<uint4*>(dst + 5 * OZ_A_PLANE) = plane_row<0>(dg);
+}
+
+// ------------------------------------------------------------------------------------------- K* digits
+// One CTA (160 threads) per candidate tile of 80: thread = (candidate cl = tid % 80, k half kc = tid / 80).
+// Per k-step the thread evaluates its 16 kernel entries per objective, turns them into digits and writes the
+// six 16-byte plane rows; the posterior-mean dot product k*.alpha is accumulated from the unquantised values.
+constexpr int OZK_ROWS = 256;
+constexpr int OZK_THREADS = 2 * OZ_TN;
+
+template <typename CT, int D, int MOBJ>
+__global__ void __launch_bounds__(OZK_THREADS, 2)
+    oz_kstar_digits_kernel(unsigned char* __restrict__ kq, double* __restrict__ meandot, const CT* __restrict__ cand,
+                           int ldc, long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk,
+                           const double* __restrict__ x, int ldx, int n, int npad, int d,
+                           const double* __restrict__ alpha, int alpha_ld, ObjParams hp) {
+  __shared__ double exp_tab[64];
+  __shared__ double xs[OZK_ROWS][(D + MOBJ) | 1];
+  __shared__ double mred[MOBJ][OZ_TN];
+  const int tid = threadIdx.x;
+  if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
+  const int ct = blockIdx.x;
+  const int cl = tid % OZ_TN, kc = tid / OZ_TN;
+  const int rg = cl >> 3, r = cl & 7;
+  const int nk_tot = npad / OZ_KS;
+
+  double cc[D];
+  {
+    long long ci = cand0 + (long long)ct * OZ_TN + cl;
+    if (ci >= n_cand) ci = n_cand - 1;  // tail tile: computed, never stored by finalize
+#pragma unroll
+    for (int k = 0; k < D; ++k) cc[k] = (k < d) ? (double)cand[ci * ldc + k] : 0.0;
+  }
+  double macc[MOBJ], coef[MOBJ], pvar[MOBJ];
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) {
+    macc[o] = 0.0;
+    coef[o] = hp.neg_half_inv_ls2[o];
+    pvar[o] = hp.prior_var[o];
+  }
+  const double kscale = 70368744177664.0;  // 2^46
+
+  for (int r0 = 0; r0 < npad; r0 += OZK_ROWS) {
+    __syncthreads();
+    for (int e = tid; e < OZK_ROWS * (D + MOBJ); e += OZK_THREADS) {
+      const int rr = e / (D + MOBJ), k = e - rr * (D + MOBJ);
+      const int row = r0 + rr;
+      double v = 0.0;
+      if (row < npad) {
+        const int rc = row < n ? row : n - 1;  // padded rows reuse the last real point (finite values)
+        if (k < D) v = (k < d) ? x[(long long)rc * ldx + k] : 0.0;
+        else v = (row < n) ? alpha[(long long)(k - D) * alpha_ld + row] : 0.0;
+      }
+      xs[rr][k] = v;
+    }
+    __syncthreads();
+    const int ks_end = min(nk_tot, (r0 + OZK_ROWS) / OZ_KS);
+    for (int ks = r0 / OZ_KS; ks < ks_end; ++ks) {
+      const int kb = ks * OZ_KS + kc * 16 - r0;
+      double sq[16];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const double* xr = xs[kb + b];
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double df = xr[k] - cc[k];
+          s = fma(df, df, s);
+        }
+        sq[b] = s;
+      }
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        unsigned long long dg[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          const double e = rbf_exp(sq[b] * coef[o], exp_tab);
+          macc[o] = fma(pvar[o] * e, xs[kb + b][D + o], macc[o]);
+          dg[b] = balanced_digits(e, kscale);
+        }
+        unsigned char* dst = kq + (((long long)o * chunk_tiles + ct) * nk_tot + ks) * OZ_B_STAGE + rg * 256 +
+                             kc * 128 + r * 16;
+        *reinterpret_cast<uint4*>(dst + 0 * OZ_B_PLANE) = plane_row<5>(dg);
+        *reinterpret_cast<uint4*>(dst + 1 * OZ_B_PLANE) = plane_row<4>(dg);
+        *reinterpret_cast<uint4*>(dst + 2 * OZ_B_PLANE) = plane_row<3>(dg);
+        *reinterpret_cast<uint4*>(dst + 3 * OZ_B_PLANE) = plane_row<2>(dg);
+        *reinterpret_cast<uint4*>(dst + 4 * OZ_B_PLANE) = plane_row<1>(dg);
+        *reinterpret_cast<uint4*>(dst + 5 * OZ_B_PLANE) = plane_row<0>(dg);
+      }
+    }
+  }
+  // mean: the two k halves of a candidate, fixed order
+  if (kc == 1) {
+#pragma unroll
+    for (int o = 0; o < MOBJ; ++o) mred[o][cl] = macc[o];
+  }
+  __syncthreads();
+  if (kc == 0) {
+#pragma unroll
+    for (int o = 0; o < MOBJ; ++o)
+      meandot[(long long)o * ld_chunk + (long long)ct * OZ_TN + cl] = macc[o] + mred[o][cl];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- tcgen05 helpers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two k halves of one MMA,
+// SBO = distance between consecutive 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
+         (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major, N, M
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TN >> 3) << 17) |
+                              ((uint32_t)(OZ_TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+// arrives on the mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+// the loaded registers are operands of the wait, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(int (&a)[OZ_PLANES][4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0][0]), "+r"(a[0][1]), "+r"(a[0][2]), "+r"(a[0][3]), "+r"(a[1][0]), "+r"(a[1][1]),
+                 "+r"(a[1][2]), "+r"(a[1][3]), "+r"(a[2][0]), "+r"(a[2][1]), "+r"(a[2][2]), "+r"(a[2][3]),
+                 "+r"(a[3][0]), "+r"(a[3][1]), "+r"(a[3][2]), "+r"(a[3][3]), "+r"(a[4][0]), "+r"(a[4][1]),
+                 "+r"(a[4][2]), "+r"(a[4][3]), "+r"(a[5][0]), "+r"(a[5][1]), "+r"(a[5][2]), "+r"(a[5][3])
+               :
+               : "memory");
+}
+
+// exact conversion of hi*256 + lo (|.| < 2^40) to FP64: build the integer next to 1.5*2^52 and subtract
+__device__ __forceinline__ double pair_to_double(int hi, int lo) {
+  const long long v = (long long)hi * 256 + (long long)lo;
+  return __longlong_as_double(v + 0x4338000000000000ll) - OZ_MAGIC;
+}
+
+// row blocks of one candidate tile are dealt to `nsplit` CTAs in serpentine order (equal k-step totals +-1 block)
+__device__ __forceinline__ int oz_row_block(int t, int r, int nsplit) {
+  return t * nsplit + ((t & 1) ? (nsplit - 1 - r) : r);
+}
+
+// ------------------------------------------------------------------------------------------- the MMA kernel
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    oz_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const unsigned char* __restrict__ wq,
+                    long long strideWq, const double* __restrict__ wscale, const unsigned char* __restrict__ kq,
+                    int npad, int nb, int nk_tot, int chunk_tiles, int nsplit, int m, int total_units,
+                    ObjParams hp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sA = smem_raw;                              // [stage][plane][4096]
+  unsigned char* sB = smem_raw + OZ_STAGES * OZ_A_STAGE;     // [stage][plane][2560]
+  double* red = reinterpret_cast<double*>(smem_raw + (size_t)OZ_STAGES * OZ_STAGE_BYTES);  // [4][80]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * OZ_TN);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)OZ_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: one lane streams k-step stages with the bulk-copy engine =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int r = u % nsplit;
+        const int o = (u / nsplit) % m;
+        const int ct = u / (nsplit * m);
+        const unsigned char* Wo = wq + (long long)o * strideWq;
+        const unsigned char* Ko = kq + ((long long)o * chunk_tiles + ct) * nk_tot * OZ_B_STAGE;
+        for (int t = 0;; ++t) {
+          const int ib = oz_row_block(t, r, nsplit);
+          if (ib >= nb) break;
+          const int nk = 4 * (ib + 1);
+          const unsigned char* At = Wo + 2LL * ib * (ib + 1) * OZ_A_STAGE;
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+            bulk_g2s(sA + stage * OZ_A_STAGE, At + (long long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
+            bulk_g2s(sB + stage * OZ_B_STAGE, Ko + (long long)ks * OZ_B_STAGE, OZ_B_STAGE, &full[stage]);
+            if (++stage == OZ_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int r = u % nsplit;
+        for (int t = 0;; ++t) {
+          const int ib = oz_row_block(t, r, nsplit);
+          if (ib >= nb) break;
+          const int nk = 4 * (ib + 1);
+          mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
+          tc_fence_after();
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a0 = sA_addr + stage * OZ_A_STAGE, b0 = sB_addr + stage * OZ_B_STAGE;
+#pragma unroll
+            for (int g = 0; g < OZ_PLANES; ++g) {
+#pragma unroll
+              for (int s = 0; s <= g; ++s) {
+                const int tt = g - s;
+                umma_i8(tmem_base + g * OZ_TN, umma_desc(a0 + s * OZ_A_PLANE), umma_desc(b0 + tt * OZ_B_PLANE),
+                        (ks > 0 || s > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == OZ_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(tmem_full);  // accumulators of this row block are complete
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t acc_phase = 0;
+    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int r = u % nsplit;
+      const int o = (u / nsplit) % m;
+      const int ct = u / (nsplit * m);
+      double ssum[OZ_TN];
+#pragma unroll
+      for (int c = 0; c < OZ_TN; ++c) ssum[c] = 0.0;
+      for (int t = 0;; ++t) {
+        const int ib = oz_row_block(t, r, nsplit);
+        if (ib >= nb) break;
+        const double f = wscale[(long long)o * npad + ib * OZ_TM + quarter * 32 + lane];
+        mbar_wait(tmem_full, acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < OZ_TN; c0 += 4) {
+          int a[OZ_PLANES][4];
+#pragma unroll
+          for (int g = 0; g < OZ_PLANES; ++g) tmem_ld4(lane_addr + g * OZ_TN + c0, a[g]);
+          tmem_ld_wait(a);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double b0 = pair_to_double(a[0][j], a[1][j]);
+            const double b1 = pair_to_double(a[2][j], a[3][j]);
+            const double b2 = pair_to_double(a[4][j], a[5][j]);
+            double v = fma(b2, 1.0 / 65536.0, b1);
+            v = fma(v, 1.0 / 65536.0, b0);
+            v *= f;
+            ssum[c0 + j] = fma(v, v, ssum[c0 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+        acc_phase ^= 1;
+      }
+      // sum over the 32 rows of this warp: transposed butterfly, 80 -> 40 -> 20 -> 10 -> 5 values per lane
+#pragma unroll
+      for (int c = 0; c < 40; ++c) {
+        const bool up = lane & 16;
+        const double send = up ? ssum[c] : ssum[c + 40];
+        const double keep = up ? ssum[c + 40] : ssum[c];
+        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        const bool up = lane & 8;
+        const double send = up ? ssum[c] : ssum[c + 20];
+        const double keep = up ? ssum[c + 20] : ssum[c];
+        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {
+        const bool up = lane & 4;
+        const double send = up ? ssum[c] : ssum[c + 10];
+        const double keep = up ? ssum[c + 10] : ssum[c];
+        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const bool up = lane & 2;
+        const double send = up ? ssum[c] : ssum[c + 5];
+        const double keep = up ? ssum[c + 5] : ssum[c];
+        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], 1);
+      // lane holds columns 40*b4 + 20*b3 + 10*b2 + 5*b1 + (0..4)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous unit's readers of `red` are done
+      if ((lane & 1) == 0) {
+        const int cbase = ((lane >> 4) & 1) * 40 + ((lane >> 3) & 1) * 20 + ((lane >> 2) & 1) * 10 +
+                          ((lane >> 1) & 1) * 5;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) red[quarter * OZ_TN + cbase + c] = ssum[c];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < OZ_TN) {
+        const double q = ((red[et] + red[OZ_TN + et]) + red[2 * OZ_TN + et]) + red[3 * OZ_TN + et];
+        const double pv = hp.prior_var[o];
+        part[((long long)o * nsplit + r) * ld_chunk + (long long)ct * OZ_TN + et] = q * pv * pv;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)OZ_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <typename CT, int D>
+int launch_oz_kstar_m(int m, dim3 grid, cudaStream_t st, unsigned char* kq, double* meandot, const CT* cand, int ldc,
+                      long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x,
+                      int ldx, int n, int npad, int d, const double* alpha, int alpha_ld, const ObjParams& hp) {
+#define BO_OZK(MO)                                                                                                 \
+  oz_kstar_digits_kernel<CT, D, MO><<<grid, OZK_THREADS, 0, st>>>(kq, meandot, cand, ldc, cand0, n_cand,           \
+                                                                   chunk_tiles, ld_chunk, x, ldx, n, npad, d, alpha, \
+                                                                   alpha_ld, hp)
+  switch (m) {
+    case 1: BO_OZK(1); break;
+    case 2: BO_OZK(2); break;
+    case 3: BO_OZK(3); break;
+    default: BO_OZK(4); break;
+  }
+#undef BO_OZK
+  BO_LAUNCH_CHECK("oz_kstar_digits_kernel");
+  return BO_OK;
+}
+
+template <typename CT>
+int launch_oz_kstar(int m, int d, dim3 grid, cudaStream_t st, unsigned char* kq, double* meandot, const CT* cand,
+                    int ldc, long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x,
+                    int ldx, int n, int npad, const double* alpha, int alpha_ld, const ObjParams& hp) {
+#define BO_OZD(DD)                                                                                                 \
+  return launch_oz_kstar_m<CT, DD>(m, grid, st, kq, meandot, cand, ldc, cand0, n_cand, chunk_tiles, ld_chunk, x,   \
+                                   ldx, n, npad, d, alpha, alpha_ld, hp)
+  if (d <= 2) BO_OZD(2);
+  if (d <= 4) BO_OZD(4);
+  if (d <= 6) BO_OZD(6);
+  if (d <= 8) BO_OZD(8);
+  if (d <= 10) BO_OZD(10);
+  if (d <= 12) BO_OZD(12);
+  BO_OZD(16);
+#undef BO_OZD
+}
+
+}  // namespace
+
+// =========================================================================================== host side
+size_t oz_wq_bytes(int n) {
+  const long long nb = round_up(n, OZ_TM) / OZ_TM;
+  return (size_t)(2 * nb * (nb + 1)) * OZ_A_STAGE;
+}
+
+int oz_quantize_w(unsigned char* wq, double* wscale, const double* wpack, int n, int m, cudaStream_t st) {
+  const int npad = round_up(n, OZ_TM), nb = npad / OZ_TM;
+  const long long strideWp = (long long)wpack_tile_offset(nb) * TILE_DOUBLES;
+  // the quantisation scale 2^(47 - e_i) lives in the second half of the caller's wscale array
+  double* qscale = wscale + (long long)m * npad;
+  oz_rowscale_kernel<<<dim3((npad + 7) / 8, m), 256, 0, st>>>(wscale, qscale, wpack, strideWp, n, npad);
+  BO_LAUNCH_CHECK("oz_rowscale_kernel");
+  const long long threads = 2LL * nb * (nb + 1) * 256;
+  oz_wdigits_kernel<<<dim3((unsigned)((threads + 255) / 256), m), 256, 0, st>>>(wq, (long long)oz_wq_bytes(n), qscale,
+                                                                                 wpack, strideWp, n, npad, nb);
+  BO_LAUNCH_CHECK("oz_wdigits_kernel");
+  return BO_OK;
+}
+
+int oz_kstar_digits(unsigned char* kq, double* meandot, const void* cand, int cand_kind, int ldc, long long cand0,
+                    long long n_cand, int tiles, int chunk_tiles, const double* x, int ldx, int n, int d, int m,
+                    const double* alpha, const ObjParams& hp, cudaStream_t st) {
+  const int npad = round_up(n, OZ_TM);
+  const long long ld_chunk = (long long)chunk_tiles * OZ_TN;
+  if (cand_kind == BO_CAND_I64)
+    return launch_oz_kstar<long long>(m, d, dim3(tiles), st, kq, meandot, static_cast<const long long*>(cand), ldc,
+                                      cand0, n_cand, chunk_tiles, ld_chunk, x, ldx, n, npad, alpha, npad, hp);
+  return launch_oz_kstar<double>(m, d, dim3(tiles), st, kq, meandot, static_cast<const double*>(cand), ldc, cand0,
+                                 n_cand, chunk_tiles, ld_chunk, x, ldx, n, npad, alpha, npad, hp);
+}
+
+int oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, const double* wscale,
+             const unsigned char* kq, int n, int m, int tiles, int chunk_tiles, int nsplit, const ObjParams& hp,
+             cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    attr_set = true;
+  }
+  const int npad = round_up(n, OZ_TM), nb = npad / OZ_TM;
+  if (nsplit > nb) nsplit = nb;
+  const int units = tiles * m * nsplit;
+  const unsigned grid = (unsigned)(units < device_sm_count() ? units : device_sm_count());
+  oz_sumsq_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(part, ld_chunk, wq, (long long)oz_wq_bytes(n), wscale, kq, npad,
+                                                     nb, npad / OZ_KS, chunk_tiles, nsplit, m, units, hp);
+  BO_LAUNCH_CHECK("oz_sumsq_kernel");
+  return BO_OK;
+}
+
+OzPlan make_oz_plan(int n, int m, long long n_cand) {
+  OzPlan p;
+  p.npad = round_up(n, OZ_TM);
+  p.nb = p.npad / OZ_TM;
+  p.nk_tot = p.npad / OZ_KS;
+  const long long tiles = (n_cand + OZ_TN - 1) / OZ_TN;
+  const int sms = device_sm_count();
+  // K* tiles that are live at the same time must fit in L2 next to W: one tile is 480 * npad bytes
+  const long long tile_bytes = (long long)OZ_PLANES * OZ_TN * p.npad;
+  long long ns = ((long long)sms * tile_bytes + (64LL << 20) - 1) / (64LL << 20);
+  if (ns < 1) ns = 1;
+  if (ns > p.nb) ns = p.nb;
+  p.nsplit = (int)ns;
+  long long ct = 8LL * sms;
+  const long long cap = (3LL << 29) / (tile_bytes * m);  // staging buffer near 1.5 GB
+  if (ct > cap) ct = cap < 1 ? 1 : cap;
+  if (ct > tiles) ct = tiles;
+  if (ct < 1) ct = 1;
+  p.chunk_tiles = (int)ct;
+  p.ld_chunk = ct * OZ_TN;
+  p.nbuf = 1;
+  p.kq_bytes = (size_t)m * ct * tile_bytes;
+  p.part_doubles = (size_t)m * p.nsplit * p.ld_chunk;
+  p.mean_doubles = (size_t)m * p.ld_chunk;
+  return p;
+}
+
+size_t oz_workspace_bytes(const OzPlan& p) {
+  return p.nbuf * (align256(p.kq_bytes) + align256(p.mean_doubles * 8)) + align256(p.part_doubles * 8);
+}
+
+int oz_score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, int ldc, long long n_cand,
+                        const double* x, int ldx, int n, int d, int m, const unsigned char* wq,
+                        const double* wscale, const double* alpha, const ObjParams& hp, double min_variance,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  const OzPlan p = make_oz_plan(n, m, n_cand);
+  if (p.npad > OZ_MAX_N) {
+    set_error("int8 engine: n = %d exceeds %d (int32 accumulator bound)", n, OZ_MAX_N);
+    return BO_ERR_INVALID;
+  }
+  if (workspace_bytes < oz_workspace_bytes(p)) {
+    set_error("int8 score workspace too small: %zu < %zu", workspace_bytes, oz_workspace_bytes(p));
+    return BO_ERR_WORKSPACE;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  unsigned char* kq = ws;
+  double* meandot = reinterpret_cast<double*>(ws + align256(p.kq_bytes));
+  double* part = reinterpret_cast<double*>(ws + align256(p.kq_bytes) + align256(p.mean_doubles * 8));
+  const long long n_chunks = (n_cand + p.ld_chunk - 1) / p.ld_chunk;
+  for (long long ci = 0; ci < n_chunks; ++ci) {
+    const long long cand0 = ci * p.ld_chunk;
+    const long long remaining = n_cand - cand0;
+    const long long live = remaining < p.ld_chunk ? remaining : p.ld_chunk;
+    const int tiles = (int)((live + OZ_TN - 1) / OZ_TN);
+    int rc = oz_kstar_digits(kq, meandot, cand, cand_kind, ldc, cand0, n_cand, tiles, p.chunk_tiles, x, ldx, n, d, m,
+                             alpha, hp, stream);
+    if (rc) return rc;
+    const bool prof = profile_enabled();
+    if (prof) profile_begin(stream);
+    rc = oz_sumsq(part, p.ld_chunk, wq, wscale, kq, n, m, tiles, p.chunk_tiles, p.nsplit, hp, stream);
+    if (prof) profile_end(stream, (double)live * m * (double)n * (double)n);
+    if (rc) return rc;
+    rc = finalize_chunk(out, cand0, n_cand, part, meandot, p.ld_chunk, tiles * OZ_TN, p.nsplit, m, hp, min_variance,
+                        stream);
+    if (rc) return rc;
+  }
+  return BO_OK;
+}
+
+}  // namespace bo

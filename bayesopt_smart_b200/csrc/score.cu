@@ -443,6 +443,16 @@ Overlap* overlap_for_current_device() {
 
 }  // namespace
 
+int finalize_chunk(const ScoreOutputs& out, long long cand0, long long n_cand, const double* part,
+                   const double* meandot, long long ld_chunk, int chunk_cands, int nb, int m, const ObjParams& hp,
+                   double min_variance, cudaStream_t stream) {
+  finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb,
+                                                                 out.acq, out.ld, cand0, n_cand, part, meandot,
+                                                                 ld_chunk, chunk_cands, nb, m, hp, min_variance);
+  BO_LAUNCH_CHECK("finalize_kernel");
+  return BO_OK;
+}
+
 ScorePlan make_score_plan(int n, int m, long long n_cand) {
   ScorePlan p;
   p.npad = round_up(n, TM);
@@ -564,11 +574,9 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     }
     BO_LAUNCH_CHECK("trmm_sumsq_kernel");
     if (ov) BO_CUDA(cudaEventRecord(ov->buffer_free[b], stream));
-    const int chunk_cands = tiles * TN;
-    finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(
-        out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld, cand0, n_cand, part, meandot[b],
-        p.ld_chunk, chunk_cands, p.nb, m, hp, min_variance);
-    BO_LAUNCH_CHECK("finalize_kernel");
+    rc = finalize_chunk(out, cand0, n_cand, part, meandot[b], p.ld_chunk, tiles * TN, p.nb, m, hp, min_variance,
+                        stream);
+    if (rc) return rc;
     if (!ov && ci + 1 < n_chunks) {
       rc = launch_kstar_chunk(ci + 1);
       if (rc) return rc;

@@ -24,6 +24,11 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
                      const ObjParams& hp, double min_variance, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream);
 
+// var = max(var0 - sum_b part[o][b][c], min_var), mu, standardise, UCB, acq for one chunk (shared by both engines)
+int finalize_chunk(const ScoreOutputs& out, long long cand0, long long n_cand, const double* part,
+                   const double* meandot, long long ld_chunk, int chunk_cands, int nb, int m, const ObjParams& hp,
+                   double min_variance, cudaStream_t stream);
+
 int acquisition_only(double* smu, double* svar, double* ucb, double* acq, const double* mu, const double* var,
                      long long ld, long long n_cand, int m, const ObjParams& hp, cudaStream_t stream);
 

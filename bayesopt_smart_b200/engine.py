@@ -12,6 +12,7 @@ arithmetic step is a kernel of libbo_b200.so reached through the C ABI.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -73,11 +74,24 @@ def candidate_kind(cand: torch.Tensor) -> int:
     raise TypeError(f"candidates must be float64 or int64, got {cand.dtype}")
 
 
-class DeviceGP:
-    """GP factor + scorer living in HBM.  One instance per process / GPU."""
+VARIANCE_ENGINES = ("dmma", "int8")
 
-    def __init__(self, device=None):
+
+class DeviceGP:
+    """GP factor + scorer living in HBM.  One instance per process / GPU.
+
+    ``variance_engine`` picks how |W k*|^2 is contracted: ``"dmma"`` (FP64 tensor cores, the default) or
+    ``"int8"`` (error-free digit splitting on tcgen05 INT8 tensor cores, ~1e-12 of the prior variance away
+    from the FP64 result).  ``BO_VARIANCE_ENGINE`` overrides the default.
+    """
+
+    def __init__(self, device=None, variance_engine: Optional[str] = None):
         self.device = device or require_cuda()
+        self.variance_engine = variance_engine or os.environ.get("BO_VARIANCE_ENGINE", "dmma")
+        if self.variance_engine not in VARIANCE_ENGINES:
+            raise ValueError(f"variance_engine must be one of {VARIANCE_ENGINES}, got {self.variance_engine!r}")
+        self.wq: Optional[torch.Tensor] = None
+        self.wscale: Optional[torch.Tensor] = None
         self.lib = _lib.load()
         self.ws = _Workspace()
         self.n = 0
@@ -109,6 +123,11 @@ class DeviceGP:
         _lib.check(self.lib.bo_gp_fit_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
                                           y.stride(0), n, d, m, pm, pv, pl, float(jitter), _ptr(ws), ws_bytes,
                                           _stream()))
+        if self.variance_engine == "int8":
+            self.wq = torch.empty(m * self.lib.bo_i8_wq_bytes(n), dtype=torch.uint8, device=self.device)
+            self.wscale = torch.empty(self.lib.bo_i8_wscale_doubles(n, m), dtype=_F64, device=self.device)
+            _lib.check(self.lib.bo_i8_quantize_w(_ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack), n, m,
+                                                 _stream()))
         self.x, self.n, self.d, self.m = x, n, d, m
         self.prior_mean = self._mean_h.copy()
         self.prior_variance = self._var_h.copy()
@@ -139,12 +158,22 @@ class DeviceGP:
                 res[key] = torch.empty(shape, dtype=_F64, device=self.device)
             else:
                 res[key] = None
-        ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
-        ws = self.ws.get("score", ws_bytes, self.device)
         _, pm = _lib.host_doubles(self.prior_mean, m)
         _, pv = _lib.host_doubles(self.prior_variance, m)
         _, pl = _lib.host_doubles(self.length_scales, m)
         bet, pb = _lib.host_doubles(betas, m)
+        if self.variance_engine == "int8":
+            ws_bytes = self.lib.bo_score_i8_workspace_bytes(self.n, m, n_cand)
+            ws = self.ws.get("score_i8", ws_bytes, self.device)
+            _lib.check(self.lib.bo_score_i8(_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]),
+                                            _ptr(res["std_var"]), _ptr(res["ucb"]), _ptr(res["acq"]), n_cand,
+                                            _ptr(cand), kind, cand.stride(0), n_cand, _ptr(self.x),
+                                            self.x.stride(0), self.n, self.d, m, _ptr(self.wq), _ptr(self.wscale),
+                                            _ptr(self.alpha), pm, pv, pl, pb, float(min_variance), _ptr(ws),
+                                            ws_bytes, _stream()))
+            return {k: v for k, v in res.items() if v is not None}
+        ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
+        ws = self.ws.get("score", ws_bytes, self.device)
         _lib.check(self.lib.bo_score_f64(_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]), _ptr(res["std_var"]),
                                          _ptr(res["ucb"]), _ptr(res["acq"]), n_cand, _ptr(cand), kind,
                                          cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0), self.n, self.d, m,

@@ -110,6 +110,36 @@ int bo_score_f64(double* mu_dev, double* var_dev, double* std_mu_dev, double* st
                  const double* length_scales_host, const double* betas_host, double min_variance,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------- a3..a8 fused, INT8 tensor-core variance engine
+ * Same contract and outputs as bo_score_f64; the triangular product |W k*|^2 is computed by error-free
+ * splitting on tcgen05.mma.kind::i8: W rows (per-row power-of-two scale) and K* entries are written as six
+ * balanced base-256 digits, the 21 digit-pair products with s + t <= 5 are accumulated exactly in int32 (TMEM)
+ * and recombined in int64 / FP64.  Truncation error of var / prior_variance: ~3e-12 at cond(K) ~ 1e7
+ * (DESIGN.md section 9), i.e. far inside the 1e-9 parity tolerance but not bit-identical to bo_score_f64.
+ *   bo_i8_quantize_w : wpack (from bo_gp_fit_f64) -> digit planes wq (m * bo_i8_wq_bytes(n) bytes) and
+ *                      row scales wscale (bo_i8_wscale_doubles(n, m) doubles).  Asynchronous on `stream`.
+ *   n <= 16384 (int32 accumulator bound).
+ * Replaces update_variance's contraction (numba_kernels.py:510-535) inside the same fused pass.     */
+size_t bo_i8_wq_bytes(int n);
+size_t bo_i8_wscale_doubles(int n, int m);
+int bo_i8_quantize_w(uint8_t* wq_dev, double* wscale_dev, const double* wpack_dev, int n, int m, void* stream);
+size_t bo_score_i8_workspace_bytes(int n, int m, long long n_cand);
+int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev, double* ucb_dev,
+                double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
+                const double* x_dev, int ldx, int n, int d, int m, const uint8_t* wq_dev, const double* wscale_dev,
+                const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
+                const double* length_scales_host, const double* betas_host, double min_variance,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+/* test hooks: the two halves of the INT8 pass on caller-owned buffers (tiles = ceil(n_cand / 80)).
+ *   kq_dev  : m * tiles * bo_npad(n) * 480 bytes of K* digit planes;  meandot_dev: (m, tiles*80) k*.alpha
+ *   q_dev   : (m, nsplit, tiles*80) partial sums of |W k*|^2 (sum over nsplit = the full quadratic form)  */
+int bo_i8_kstar_digits(uint8_t* kq_dev, double* meandot_dev, const void* cand_dev, int cand_kind, int ldc,
+                       long long n_cand, const double* x_dev, int ldx, int n, int d, int m,
+                       const double* alpha_dev, const double* prior_variance_host,
+                       const double* length_scales_host, void* stream);
+int bo_i8_sumsq(double* q_dev, const uint8_t* wq_dev, const double* wscale_dev, const uint8_t* kq_dev, int n, int m,
+                long long n_cand, int nsplit, const double* prior_variance_host, void* stream);
+
 /* ----------------------------------------------------- a6..a8 stand-alone (HBM bound)
  * standardize_objectives + update_ucb + update_hypervolume_improvement on existing
  * (m, ld) mu / var arrays.  Outputs may be NULL.  numba_kernels.py:538-570,
