@@ -368,9 +368,9 @@ int bo_i8_kstar_digits(uint8_t* kq_dev, double* meandot_dev, const void* cand_de
   ObjParams hp;
   int rc = make_params(&hp, m, nullptr, prior_variance_host, length_scales_host, nullptr);
   if (rc) return rc;
-  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN);
-  return oz_kstar_digits(kq_dev, meandot_dev, cand_dev, cand_kind, ldc, 0, n_cand, tiles, tiles, x_dev, ldx, n, d, m,
-                         alpha_dev, hp, (cudaStream_t)stream);
+  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN), alloc_tiles = (tiles + 3) / 4 * 4;
+  return oz_kstar_digits(kq_dev, meandot_dev, cand_dev, cand_kind, ldc, 0, n_cand, tiles, alloc_tiles, x_dev, ldx, n,
+                         d, m, alpha_dev, hp, (cudaStream_t)stream);
 }
 
 int bo_i8_sumsq(double* q_dev, const uint8_t* wq_dev, const double* wscale_dev, const uint8_t* kq_dev, int n, int m,
@@ -381,9 +381,9 @@ int bo_i8_sumsq(double* q_dev, const uint8_t* wq_dev, const double* wscale_dev, 
   ObjParams hp;
   int rc = make_params(&hp, m, nullptr, prior_variance_host, nullptr, nullptr);
   if (rc) return rc;
-  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN);
-  return oz_sumsq(q_dev, (long long)tiles * OZ_TN, wq_dev, wscale_dev, kq_dev, n, m, tiles, tiles, nsplit, hp,
-                  (cudaStream_t)stream);
+  const int tiles = (int)((n_cand + OZ_TN - 1) / OZ_TN), alloc_tiles = (tiles + 3) / 4 * 4;
+  return oz_sumsq(q_dev, (long long)alloc_tiles * OZ_TN, wq_dev, wscale_dev, kq_dev, n, m, tiles, alloc_tiles, nsplit,
+                  hp, (cudaStream_t)stream);
 }
 
 int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* acq_dev,

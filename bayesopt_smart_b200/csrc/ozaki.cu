@@ -9,7 +9,7 @@
 // digits are the bytes of (q + 0x8080808080) with the low five XORed by 0x80.  With balanced digits the dropped
 // pairs (s + t >= 6) are zero-mean, which is worth two digits of accuracy over unsigned slices.
 //   V_i = pvar 2^(e_i-13) sum_{g=0..5} 256^-g acc_g,   acc_g = sum_{s+t=g} sum_k dW_s[i,k] dK_t[k,c]   (exact int32)
-//       = pvar 2^(e_i-21) (b_0 + 2^-16 b_1 + 2^-32 b_2),  b_j = 256 acc_2j + acc_2j+1             (exact int64)
+//       = pvar 2^(e_i-29) (b_0 + 2^-24 b_1),  b_j = (256 acc_3j + acc_3j+1) 256 + acc_3j+2          (exact int64)
 //
 // Layout.  Both operands are stored in HBM exactly as the UMMA canonical K-major / no-swizzle shared-memory
 // image of one k-step (32 k), all six planes of a (row block | candidate tile) contiguous:
@@ -17,11 +17,17 @@
 // so one cp.async.bulk per operand per k-step fills a pipeline stage, and the smem descriptor is
 // (start, LBO = 128 B between the two k halves, SBO = 256 B between row groups).
 //
-// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warp 1: TMEM allocator + single-thread
-// MMA issuer (21 MMAs 128x80x32 per k-step into 6 TMEM accumulators = 480 columns); warps 2-5: epilogue
-// (tcgen05.ld, pairwise integer recombination a_2j*256 + a_2j+1, three exact int64 -> FP64 conversions, row
-// scale, square, running per-thread sums over all row blocks of the work unit; one transposed shuffle
-// reduction per unit).
+// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warp 1: TMEM allocator + MMA issuer; warps
+// 2-9: epilogue, two warps per TMEM lane quarter with 32 columns each (tcgen05.ld, integer recombination in
+// triples, two exact int64 -> FP64 conversions, row scale, square, running per-thread sums over all row blocks
+// of the work unit; one transposed shuffle reduction per unit).
+// The W planes are the MMA's A operand and are read from TENSOR MEMORY: with A in shared memory a 128 x N x 32
+// kind::i8 MMA takes N/2 + 43 cycles on B200 (the 4 KB A read is not hidden: tools/umma_probe.cu), from TMEM it
+// takes N/2.  Per k-step the eight epilogue warps (idle during the k loop) move the six 4 KB A planes shared
+// memory -> registers -> TMEM (ld.shared.v4 + tcgen05.st.32x32b.x8, two alternating 48-column slots) and the
+// issuing thread runs the 21 MMAs 128x64x32 into the 6 accumulators (384 columns).  tcgen05.cp from the
+// issuing thread was measured and rejected: it shares the in-order pipe with the MMAs (939 vs 672 cycles per
+// k-step, tools/umma_probe2.cu; the register path: 845 with the handshake, tools/umma_probe3.cu).
 #include "ozaki.cuh"
 
 #include <stdlib.h>
@@ -33,11 +39,14 @@ namespace bo {
 namespace {
 
 constexpr int OZ_STAGES = 5;
-constexpr int OZ_THREADS = 192;
-constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 39936
+constexpr int OZ_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int OZ_EC = OZ_TN / 2;     // accumulator columns per epilogue warp
+constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 36864
+constexpr int OZ_ASLOT_COL = OZ_PLANES * OZ_TN;          // first TMEM column of the two A-operand slots
+constexpr int OZ_ASLOT_COLS = OZ_PLANES * (OZ_KS / 4);   // 48 columns: six planes of 128 lanes x 32 bytes
 constexpr int OZ_TMEM_COLS = 512;
 constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_TN * sizeof(double) +
-                           (2 * OZ_STAGES + 2) * sizeof(uint64_t) + 16;
+                           (2 * OZ_STAGES + 4) * sizeof(uint64_t) + 16;
 
 constexpr unsigned long long OZ_BIAS = 0x0000008080808080ull;  // 0x80 in each of the five low digit bytes
 constexpr double OZ_MAGIC = 6755399441055744.0;                // 1.5 * 2^52
@@ -93,7 +102,7 @@ __global__ void oz_rowscale_kernel(double* __restrict__ wscale, double* __restri
     if (mx > 0.0 && mx < 1e300) {
       int e;
       frexp(mx * (128.0 / 126.0), &e);  // value = f 2^e, f in [0.5, 1)  =>  value <= 2^e
-      ws = ldexp(1.0, e - 21);  // 2^(e-13) for sum_g 256^-g acc_g, times 2^-8 for the pairwise recombination
+      ws = ldexp(1.0, e - 29);  // 2^(e-13) for sum_g 256^-g acc_g, times 2^-16 for the recombination in triples
       qs = ldexp(1.0, 47 - e);
     }
     wscale[(long long)o * npad + row] = ws;
@@ -138,7 +147,7 @@ __global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long stri
 }
 
 // ------------------------------------------------------------------------------------------- K* digits
-// One CTA (160 threads) per candidate tile of 80: thread = (candidate cl = tid % 80, k half kc = tid / 80).
+// One CTA (128 threads) per candidate tile of 64: thread = (candidate cl = tid % 64, k half kc = tid / 64).
 // Per k-step the thread evaluates its 16 kernel entries per objective, turns them into digits and writes the
 // six 16-byte plane rows; the posterior-mean dot product k*.alpha is accumulated from the unquantised values.
 constexpr int OZK_ROWS = 256;
@@ -242,25 +251,39 @@ __global__ void __launch_bounds__(OZK_THREADS, 2)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two k halves of one MMA,
-// SBO = distance between consecutive 8-row groups (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
-         (1ull << 46);
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1), K-major, no swizzle: 8-row x 16-byte
+// core matrices; LBO = 128 B between the two k halves of one MMA, SBO = 256 B between consecutive 8-row groups.
+// Built from a precomputed low word ((address >> 4) | LBO << 16); the high word is constant.
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
+  return (uint64_t)lo | ((uint64_t)((256u >> 4) | (1u << 14)) << 32);
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major, N, M
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TN >> 3) << 17) |
                               ((uint32_t)(OZ_TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// A operand (128 lanes x 8 columns = 128 rows x 32 bytes) from tensor memory
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+      "r"(tmem_a), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
       : "memory");
 }
 
@@ -286,10 +309,35 @@ __device__ __forceinline__ void tmem_ld_wait(int (&a)[OZ_PLANES][4]) {
                : "memory");
 }
 
-// exact conversion of hi*256 + lo (|.| < 2^40) to FP64: build the integer next to 1.5*2^52 and subtract
-__device__ __forceinline__ double pair_to_double(int hi, int lo) {
-  const long long v = (long long)hi * 256 + (long long)lo;
+// exact conversion of (a*256 + b)*256 + c (|.| < 2^48) to FP64: build the integer next to 1.5*2^52 and subtract
+__device__ __forceinline__ double triple_to_double(int a, int b, int c) {
+  const long long v = ((long long)a * 256 + (long long)b) * 256 + (long long)c;
   return __longlong_as_double(v + 0x4338000000000000ll) - OZ_MAGIC;
+}
+
+// multicast variants for a cluster of CTAs that walk the same W row blocks on different candidate tiles
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                            uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], "
+      "%4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // row blocks of one candidate tile are dealt to `nsplit` CTAs in serpentine order (equal k-step totals +-1 block)
@@ -298,6 +346,48 @@ __device__ __forceinline__ int oz_row_block(int t, int r, int nsplit) {
 }
 
 // ------------------------------------------------------------------------------------------- the MMA kernel
+// position of a role in the persistent schedule: work unit u -> its row blocks (serpentine order) -> k-steps
+struct OzCursor {
+  int u, t, ib, nk, ks;
+  bool valid;
+};
+__device__ __forceinline__ void oz_cursor_init(OzCursor& c, int first_unit, int total_units, int nsplit) {
+  c.u = first_unit;
+  c.t = 0;
+  c.ks = 0;
+  c.valid = first_unit < total_units;
+  c.ib = c.valid ? oz_row_block(0, c.u % nsplit, nsplit) : 0;
+  c.nk = 4 * (c.ib + 1);
+}
+// next row block (returns true when that crosses into a new work unit)
+__device__ __forceinline__ bool oz_cursor_next_block(OzCursor& c, int stride, int total_units, int nsplit, int nb) {
+  bool new_unit = false;
+  ++c.t;
+  int ib = oz_row_block(c.t, c.u % nsplit, nsplit);
+  if (ib >= nb) {
+    c.u += stride;
+    c.t = 0;
+    new_unit = true;
+    c.valid = c.u < total_units;
+    ib = c.valid ? oz_row_block(0, c.u % nsplit, nsplit) : 0;
+  }
+  c.ib = ib;
+  c.nk = 4 * (ib + 1);
+  c.ks = 0;
+  return new_unit;
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(lo.x),
+               "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
+// CL = CTAs per cluster.  The CTAs of a cluster take CL consecutive candidate tiles of the same (objective, row
+// split): they need the same W k-steps at the same time, so each CTA fetches 1/CL of every W stage and
+// multicasts it into all CL shared memories.  (Measured: no gain on B200 -- the pass is not L2-bound -- so the
+// default is CL = 1; BO_I8_CLUSTER=2|4 selects the multicast variants.)
+template <int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const unsigned char* __restrict__ wq,
                     long long strideWq, const double* __restrict__ wscale, const unsigned char* __restrict__ kq,
@@ -305,11 +395,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                     ObjParams hp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sA = smem_raw;                              // [stage][plane][4096]
-  unsigned char* sB = smem_raw + OZ_STAGES * OZ_A_STAGE;     // [stage][plane][2560]
-  double* red = reinterpret_cast<double*>(smem_raw + (size_t)OZ_STAGES * OZ_STAGE_BYTES);  // [4][80]
+  unsigned char* sB = smem_raw + OZ_STAGES * OZ_A_STAGE;     // [stage][plane][2048]
+  double* red = reinterpret_cast<double*>(smem_raw + (size_t)OZ_STAGES * OZ_STAGE_BYTES);  // [4][64]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * OZ_TN);
   uint64_t* empty = full + OZ_STAGES;
-  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* a_ready = empty + OZ_STAGES;  // [2]: the A slot holds the planes of its k-step
+  uint64_t* tmem_full = a_ready + 2;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
@@ -318,10 +409,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);  // one commit from the MMA warp of every CTA in the cluster
     }
+    mbar_init(&a_ready[0], 8);
+    mbar_init(&a_ready[1], 8);
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, 8);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -332,167 +425,183 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer copies into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = CL > 1 ? (int)cluster_rank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     // ===== producer: one lane streams k-step stages with the bulk-copy engine =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int r = u % nsplit;
-        const int o = (u / nsplit) % m;
-        const int ct = u / (nsplit * m);
-        const unsigned char* Wo = wq + (long long)o * strideWq;
+      OzCursor c;
+      for (oz_cursor_init(c, cluster_id, total_units, nsplit); c.valid;
+           oz_cursor_next_block(c, n_clusters, total_units, nsplit, nb)) {
+        const int o = (c.u / nsplit) % m;
+        const int ct = (c.u / (nsplit * m)) * CL + crank;
+        const unsigned char* At = wq + (long long)o * strideWq + 2LL * c.ib * (c.ib + 1) * OZ_A_STAGE;
         const unsigned char* Ko = kq + ((long long)o * chunk_tiles + ct) * nk_tot * OZ_B_STAGE;
-        for (int t = 0;; ++t) {
-          const int ib = oz_row_block(t, r, nsplit);
-          if (ib >= nb) break;
-          const int nk = 4 * (ib + 1);
-          const unsigned char* At = Wo + 2LL * ib * (ib + 1) * OZ_A_STAGE;
-          for (int ks = 0; ks < nk; ++ks) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+        for (int ks = 0; ks < c.nk; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+          if (CL == 1) {
             bulk_g2s(sA + stage * OZ_A_STAGE, At + (long long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
-            bulk_g2s(sB + stage * OZ_B_STAGE, Ko + (long long)ks * OZ_B_STAGE, OZ_B_STAGE, &full[stage]);
-            if (++stage == OZ_STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+          } else {
+            constexpr int kSlice = OZ_A_STAGE / CL;
+            bulk_g2s_mc(sA + stage * OZ_A_STAGE + crank * kSlice, At + (long long)ks * OZ_A_STAGE + crank * kSlice,
+                        kSlice, &full[stage], kMask);
+          }
+          bulk_g2s(sB + stage * OZ_B_STAGE, Ko + (long long)ks * OZ_B_STAGE, OZ_B_STAGE, &full[stage]);
+          if (++stage == OZ_STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int r = u % nsplit;
-        for (int t = 0;; ++t) {
-          const int ib = oz_row_block(t, r, nsplit);
-          if (ib >= nb) break;
-          const int nk = 4 * (ib + 1);
-          mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
-          tc_fence_after();
-          for (int ks = 0; ks < nk; ++ks) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a0 = sA_addr + stage * OZ_A_STAGE, b0 = sB_addr + stage * OZ_B_STAGE;
+    // ===== MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps the descriptors in
+    // uniform registers); one elected lane issues the MMAs and the commits.  Nothing but the a_ready wait, one
+    // fence and the commit sits between two batches of 21 MMAs: the tensor pipe buffers ~1 instruction, so every
+    // other instruction in this thread is a bubble (tools/umma_probe2.cu: try_wait 115, fence 48, commit 52 clk) =====
+    int stage = 0;
+    uint32_t acc_phase = 0, g = 0;  // g: k-steps issued so far (A slot = g & 1)
+    const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    OzCursor c;
+    for (oz_cursor_init(c, cluster_id, total_units, nsplit); c.valid;
+         oz_cursor_next_block(c, n_clusters, total_units, nsplit, nb)) {
+      mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
+      for (int ks = 0; ks < c.nk; ++ks, ++g) {
+        mbar_wait(&a_ready[g & 1], (g >> 1) & 1);  // feeders saw full[stage] and filled the A slot
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_lo = b_lo0 + stage * (OZ_B_STAGE >> 4);
+          const uint32_t first = ks > 0 ? 1u : 0u;
+          const uint32_t a_tm = tmem_base + OZ_ASLOT_COL + (g & 1) * OZ_ASLOT_COLS;
 #pragma unroll
-            for (int g = 0; g < OZ_PLANES; ++g) {
+          for (int gg = 0; gg < OZ_PLANES; ++gg) {
 #pragma unroll
-              for (int s = 0; s <= g; ++s) {
-                const int tt = g - s;
-                umma_i8(tmem_base + g * OZ_TN, umma_desc(a0 + s * OZ_A_PLANE), umma_desc(b0 + tt * OZ_B_PLANE),
-                        (ks > 0 || s > 0) ? 1u : 0u);
-              }
-            }
-            umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
-            if (++stage == OZ_STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+            for (int s = 0; s <= gg; ++s)
+              umma_i8_ts(tmem_base + gg * OZ_TN, a_tm + s * (OZ_KS / 4),
+                         umma_desc_lo(b_lo + (gg - s) * (OZ_B_PLANE >> 4)), s > 0 ? 1u : first);
           }
-          umma_commit(tmem_full);  // accumulators of this row block are complete
-          acc_phase ^= 1;
+          // frees the smem stage (in every CTA of the cluster) and this A slot once the MMAs have read them
+          if (CL == 1) umma_commit(&empty[stage]);
+          else umma_commit_mc(&empty[stage], kMask);
+          if (ks == c.nk - 1) umma_commit(tmem_full);  // accumulators of this row block are complete
         }
+        __syncwarp();
+        if (++stage == OZ_STAGES) stage = 0;
       }
+      acc_phase ^= 1;
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-    const int quarter = warp & 3;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // ===== warps 2..9: A-operand feeders during the k loop, epilogue at the end of every row block.
+    // TMEM lane quarter = warp % 4 (row = quarter*32 + lane); half = (warp - 2) / 4 picks planes 3*half..3*half+2
+    // when feeding and accumulator columns half*32..half*32+31 when draining. =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t acc_addr = lane_base + half * OZ_EC;
+    const int row = quarter * 32 + lane;
+    const unsigned char* a_src = sA + (half * 3) * OZ_A_PLANE + (row >> 3) * 256 + (row & 7) * 16;
+    const int et = threadIdx.x - 64;  // 0..255 among these threads
     uint32_t acc_phase = 0;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int r = u % nsplit;
-      const int o = (u / nsplit) % m;
-      const int ct = u / (nsplit * m);
-      double ssum[OZ_TN];
+    uint32_t fed = 0;        // k-steps fed so far (global count: stage = fed % STAGES, slot = fed & 1)
+    uint32_t drain_end = 0;  // global index one past the last k-step of the row block being drained
+    OzCursor fc, dc;         // feeding runs up to two k-steps ahead of draining
+    oz_cursor_init(fc, cluster_id, total_units, nsplit);
+    oz_cursor_init(dc, cluster_id, total_units, nsplit);
+    double ssum[OZ_EC];
 #pragma unroll
-      for (int c = 0; c < OZ_TN; ++c) ssum[c] = 0.0;
-      for (int t = 0;; ++t) {
-        const int ib = oz_row_block(t, r, nsplit);
-        if (ib >= nb) break;
-        const double f = wscale[(long long)o * npad + ib * OZ_TM + quarter * 32 + lane];
-        mbar_wait(tmem_full, acc_phase);
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < OZ_TN; c0 += 4) {
-          int a[OZ_PLANES][4];
-#pragma unroll
-          for (int g = 0; g < OZ_PLANES; ++g) tmem_ld4(lane_addr + g * OZ_TN + c0, a[g]);
-          tmem_ld_wait(a);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double b0 = pair_to_double(a[0][j], a[1][j]);
-            const double b1 = pair_to_double(a[2][j], a[3][j]);
-            const double b2 = pair_to_double(a[4][j], a[5][j]);
-            double v = fma(b2, 1.0 / 65536.0, b1);
-            v = fma(v, 1.0 / 65536.0, b0);
-            v *= f;
-            ssum[c0 + j] = fma(v, v, ssum[c0 + j]);
-          }
+    for (int c = 0; c < OZ_EC; ++c) ssum[c] = 0.0;
+    while (dc.valid) {
+      drain_end += dc.nk;
+      // ---- feed every k-step of this row block and the first two of the next (their slots are free as soon as
+      // the last MMAs of this block have completed, i.e. while the accumulators are being drained)
+      while (fc.valid && fed < drain_end + 2) {
+        const int stage = fed % OZ_STAGES;
+        mbar_wait(&full[stage], (fed / OZ_STAGES) & 1);  // TMA has landed the stage
+        if (fed >= 2) {
+          const uint32_t j = fed - 2;  // the k-step that used this A slot: its MMAs signal empty[its stage]
+          mbar_wait(&empty[j % OZ_STAGES], (j / OZ_STAGES) & 1);
+          tc_fence_after();
         }
+        const unsigned char* src = a_src + stage * OZ_A_STAGE;
+        const uint32_t dst = lane_base + OZ_ASLOT_COL + (fed & 1) * OZ_ASLOT_COLS + (half * 3) * (OZ_KS / 4);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint4 lo = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE);        // k 0..15 of the row
+          const uint4 hi = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE + 128);  // k 16..31
+          tmem_st8(dst + p * (OZ_KS / 4), lo, hi);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
-        acc_phase ^= 1;
+        if (lane == 0) mbar_arrive(&a_ready[fed & 1]);
+        ++fed;
+        if (++fc.ks == fc.nk) oz_cursor_next_block(fc, n_clusters, total_units, nsplit, nb);
       }
-      // sum over the 32 rows of this warp: transposed butterfly, 80 -> 40 -> 20 -> 10 -> 5 values per lane
+      // ---- drain the accumulators of row block dc
+      const int r = dc.u % nsplit;
+      const int o = (dc.u / nsplit) % m;
+      const int ct = (dc.u / (nsplit * m)) * CL + crank;
+      const double f = wscale[(long long)o * npad + dc.ib * OZ_TM + row];
+      const double f24 = f * (1.0 / 16777216.0);
+      mbar_wait(tmem_full, acc_phase);
+      tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 40; ++c) {
-        const bool up = lane & 16;
-        const double send = up ? ssum[c] : ssum[c + 40];
-        const double keep = up ? ssum[c + 40] : ssum[c];
-        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      for (int c0 = 0; c0 < OZ_EC; c0 += 4) {
+        int a[OZ_PLANES][4];
+#pragma unroll
+        for (int gq = 0; gq < OZ_PLANES; ++gq) tmem_ld4(acc_addr + gq * OZ_TN + c0, a[gq]);
+        tmem_ld_wait(a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // V = f (b0 + 2^-24 b1),  b0 = (a0 256 + a1) 256 + a2,  b1 = (a3 256 + a4) 256 + a5   (exact int64)
+          const double b0 = triple_to_double(a[0][j], a[1][j], a[2][j]);
+          const double b1 = triple_to_double(a[3][j], a[4][j], a[5][j]);
+          const double v = fma(b1, f24, b0 * f);
+          ssum[c0 + j] = fma(v, v, ssum[c0 + j]);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      acc_phase ^= 1;
+      const bool unit_done = oz_cursor_next_block(dc, n_clusters, total_units, nsplit, nb);
+      if (unit_done) {
+        // sum over the 32 rows of this warp: transposed butterfly, 32 -> 16 -> 8 -> 4 -> 2 -> 1 values per lane;
+        // lane L ends up with the sum of column half*32 + L
 #pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        const bool up = lane & 8;
-        const double send = up ? ssum[c] : ssum[c + 20];
-        const double keep = up ? ssum[c + 20] : ssum[c];
-        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
+        for (int w = OZ_EC / 2; w >= 1; w >>= 1) {
 #pragma unroll
-      for (int c = 0; c < 10; ++c) {
-        const bool up = lane & 4;
-        const double send = up ? ssum[c] : ssum[c + 10];
-        const double keep = up ? ssum[c + 10] : ssum[c];
-        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
+          for (int c = 0; c < w; ++c) {
+            const bool up = lane & w;
+            const double send = up ? ssum[c] : ssum[c + w];
+            const double keep = up ? ssum[c + w] : ssum[c];
+            ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous unit's readers of `red` are done
+        red[quarter * OZ_TN + half * OZ_EC + lane] = ssum[0];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < OZ_TN) {
+          const double q = ((red[et] + red[OZ_TN + et]) + red[2 * OZ_TN + et]) + red[3 * OZ_TN + et];
+          const double pv = hp.prior_var[o];
+          part[((long long)o * nsplit + r) * ld_chunk + (long long)ct * OZ_TN + et] = q * pv * pv;
+        }
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const bool up = lane & 2;
-        const double send = up ? ssum[c] : ssum[c + 5];
-        const double keep = up ? ssum[c + 5] : ssum[c];
-        ssum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-#pragma unroll
-      for (int c = 0; c < 5; ++c) ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], 1);
-      // lane holds columns 40*b4 + 20*b3 + 10*b2 + 5*b1 + (0..4)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous unit's readers of `red` are done
-      if ((lane & 1) == 0) {
-        const int cbase = ((lane >> 4) & 1) * 40 + ((lane >> 3) & 1) * 20 + ((lane >> 2) & 1) * 10 +
-                          ((lane >> 1) & 1) * 5;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) red[quarter * OZ_TN + cbase + c] = ssum[c];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < OZ_TN) {
-        const double q = ((red[et] + red[OZ_TN + et]) + red[2 * OZ_TN + et]) + red[3 * OZ_TN + et];
-        const double pv = hp.prior_var[o];
-        part[((long long)o * nsplit + r) * ld_chunk + (long long)ct * OZ_TN + et] = q * pv * pv;
+        for (int c = 0; c < OZ_EC; ++c) ssum[c] = 0.0;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -571,22 +680,83 @@ int oz_kstar_digits(unsigned char* kq, double* meandot, const void* cand, int ca
                                  n_cand, chunk_tiles, ld_chunk, x, ldx, n, npad, alpha, npad, hp);
 }
 
+namespace {
+
+int oz_cluster_size() {
+  static const int cl = [] {
+    const char* e = getenv("BO_I8_CLUSTER");
+    const int v = e ? atoi(e) : 1;
+    return (v == 1 || v == 2 || v == 4) ? v : 1;
+  }();
+  return cl;
+}
+
+template <int CL>
+int launch_oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, long long strideWq,
+                    const double* wscale, const unsigned char* kq, int npad, int nb, int chunk_tiles, int nsplit,
+                    int m, int tiles, const ObjParams& hp, cudaStream_t st) {
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  if (!attr_set) {
+    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    max_clusters = device_sm_count() / CL;
+    if (CL > 1) {
+      // how many clusters of CL one-CTA-per-SM blocks the GPCs can hold at once
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(device_sm_count() / CL * CL);
+      q.blockDim = dim3(OZ_THREADS);
+      q.dynamicSmemBytes = OZ_SMEM;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = CL;
+      a[0].val.clusterDim.y = 1;
+      a[0].val.clusterDim.z = 1;
+      q.attrs = a;
+      q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, oz_sumsq_kernel<CL>, &q) == cudaSuccess && nc > 0) max_clusters = nc;
+      cudaGetLastError();
+    }
+    attr_set = true;
+  }
+  const int groups = (tiles + CL - 1) / CL;
+  const int units = groups * m * nsplit;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = OZ_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  BO_CUDA(cudaLaunchKernelEx(&cfg, oz_sumsq_kernel<CL>, part, ld_chunk, wq, strideWq, wscale, kq, npad, nb,
+                             npad / OZ_KS, chunk_tiles, nsplit, m, units, hp));
+  BO_LAUNCH_CHECK("oz_sumsq_kernel");
+  return BO_OK;
+}
+
+}  // namespace
+
+// `chunk_tiles` (the K* / part allocation) must be a multiple of the cluster size: a cluster always walks CL
+// tiles, the ones beyond `tiles` read allocated-but-unwritten digits and their sums are never used.
 int oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, const double* wscale,
              const unsigned char* kq, int n, int m, int tiles, int chunk_tiles, int nsplit, const ObjParams& hp,
              cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    attr_set = true;
-  }
   const int npad = round_up(n, OZ_TM), nb = npad / OZ_TM;
   if (nsplit > nb) nsplit = nb;
-  const int units = tiles * m * nsplit;
-  const unsigned grid = (unsigned)(units < device_sm_count() ? units : device_sm_count());
-  oz_sumsq_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(part, ld_chunk, wq, (long long)oz_wq_bytes(n), wscale, kq, npad,
-                                                     nb, npad / OZ_KS, chunk_tiles, nsplit, m, units, hp);
-  BO_LAUNCH_CHECK("oz_sumsq_kernel");
-  return BO_OK;
+  int cl = oz_cluster_size();
+  while (cl > 1 && chunk_tiles % cl != 0) cl >>= 1;
+  const long long strideWq = (long long)oz_wq_bytes(n);
+  switch (cl) {
+    case 4: return launch_oz_sumsq<4>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
+    case 2: return launch_oz_sumsq<2>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
+    default: return launch_oz_sumsq<1>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
+  }
 }
 
 OzPlan make_oz_plan(int n, int m, long long n_cand) {
@@ -596,7 +766,7 @@ OzPlan make_oz_plan(int n, int m, long long n_cand) {
   p.nk_tot = p.npad / OZ_KS;
   const long long tiles = (n_cand + OZ_TN - 1) / OZ_TN;
   const int sms = device_sm_count();
-  // K* tiles that are live at the same time must fit in L2 next to W: one tile is 480 * npad bytes
+  // K* tiles that are live at the same time must fit in L2 next to W: one tile is 6 * 64 * npad bytes
   const long long tile_bytes = (long long)OZ_PLANES * OZ_TN * p.npad;
   long long ns = ((long long)sms * tile_bytes + (64LL << 20) - 1) / (64LL << 20);
   if (ns < 1) ns = 1;
@@ -607,6 +777,7 @@ OzPlan make_oz_plan(int n, int m, long long n_cand) {
   if (ct > cap) ct = cap < 1 ? 1 : cap;
   if (ct > tiles) ct = tiles;
   if (ct < 1) ct = 1;
+  ct = (ct + 3) / 4 * 4;  // whole clusters of candidate tiles (oz_sumsq)
   p.chunk_tiles = (int)ct;
   p.ld_chunk = ct * OZ_TN;
   p.nbuf = 1;

@@ -13,28 +13,28 @@ namespace bo {
 
 constexpr int OZ_PLANES = 6;   // digits per operand element
 constexpr int OZ_TM = 128;     // W rows per row block  (UMMA M, TMEM lanes)
-constexpr int OZ_TN = 80;      // candidates per tile   (UMMA N, TMEM columns per accumulator)
+constexpr int OZ_TN = 64;      // candidates per tile   (UMMA N, TMEM columns per accumulator)
 constexpr int OZ_KS = 32;      // k depth of one tcgen05.mma.kind::i8
 constexpr int OZ_A_PLANE = OZ_TM * OZ_KS;              // 4096 B
-constexpr int OZ_B_PLANE = OZ_TN * OZ_KS;              // 2560 B
+constexpr int OZ_B_PLANE = OZ_TN * OZ_KS;              // 2048 B
 constexpr int OZ_A_STAGE = OZ_PLANES * OZ_A_PLANE;     // 24576 B: one k-step of a W row block, all planes
-constexpr int OZ_B_STAGE = OZ_PLANES * OZ_B_PLANE;     // 15360 B: one k-step of a K* tile, all planes
+constexpr int OZ_B_STAGE = OZ_PLANES * OZ_B_PLANE;     // 12288 B: one k-step of a K* tile, all planes
 constexpr int OZ_MAX_N = 16384;  // int32 accumulators: 6 pairs * 2^14 * npad < 2^31
 
 struct OzPlan {
   int npad = 0, nb = 0, nk_tot = 0;
   int nsplit = 1;           // row blocks of one candidate tile are dealt to nsplit CTAs (keeps K* tiles in L2)
-  int chunk_tiles = 0;      // candidate tiles (of 80) per chunk
-  long long ld_chunk = 0;   // chunk_tiles * 80
+  int chunk_tiles = 0;      // candidate tiles (of 64) per chunk
+  long long ld_chunk = 0;   // chunk_tiles * 64
   int nbuf = 1;
   size_t kq_bytes = 0, part_doubles = 0, mean_doubles = 0;
 };
 OzPlan make_oz_plan(int n, int m, long long n_cand);
 size_t oz_workspace_bytes(const OzPlan& p);
 
-// bytes of the digit planes of W for ONE objective; wscale holds npad doubles per objective
+// bytes of the digit planes of W for ONE objective; wscale holds 2 * m * npad doubles (row scales, then the quantisation scales)
 size_t oz_wq_bytes(int n);
-// wpack (DMMA tile order, from bo_gp_fit_f64) -> digit planes + per-row scale 2^(e_i - 13)
+// wpack (DMMA tile order, from bo_gp_fit_f64) -> digit planes + per-row scale 2^(e_i - 29)
 int oz_quantize_w(unsigned char* wq, double* wscale, const double* wpack, int n, int m, cudaStream_t st);
 
 // the scoring pass with the INT8 engine (same contract as score_candidates)

@@ -130,9 +130,9 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
                 const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
                 const double* length_scales_host, const double* betas_host, double min_variance,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
-/* test hooks: the two halves of the INT8 pass on caller-owned buffers (tiles = ceil(n_cand / 80)).
- *   kq_dev  : m * tiles * bo_npad(n) * 480 bytes of K* digit planes;  meandot_dev: (m, tiles*80) k*.alpha
- *   q_dev   : (m, nsplit, tiles*80) partial sums of |W k*|^2 (sum over nsplit = the full quadratic form)  */
+/* test hooks: the two halves of the INT8 pass on caller-owned buffers (tiles = ceil(n_cand / 64) rounded up to a multiple of 4).
+ *   kq_dev  : m * tiles * bo_npad(n) * 384 bytes of K* digit planes;  meandot_dev: (m, tiles*64) k*.alpha
+ *   q_dev   : (m, nsplit, tiles*64) partial sums of |W k*|^2 (sum over nsplit = the full quadratic form)  */
 int bo_i8_kstar_digits(uint8_t* kq_dev, double* meandot_dev, const void* cand_dev, int cand_kind, int ldc,
                        long long n_cand, const double* x_dev, int ldx, int n, int d, int m,
                        const double* alpha_dev, const double* prior_variance_host,

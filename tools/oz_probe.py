@@ -78,7 +78,7 @@ def main():
         e = np.zeros(npad, dtype=np.int64)
         nz = mx > 0
         e[nz] = np.frexp(mx[nz] * (128.0 / 126.0))[1]
-        ws_ref = np.where(nz, np.ldexp(1.0, e - 21), 0.0)
+        ws_ref = np.where(nz, np.ldexp(1.0, e - 29), 0.0)
         q = np.rint(W * np.where(nz, np.ldexp(1.0, 47 - e), 0.0)[:, None]).astype(np.int64)
         dig = balanced(q)
         # GPU planes: per row block ib, k-steps 0..4(ib+1)-1
@@ -95,9 +95,10 @@ def main():
         Wd.append(got)
 
     # ---- K* digits
-    tiles = (n_cand + 79) // 80
-    kq = torch.zeros(m * tiles * npad * 480, dtype=torch.uint8, device="cuda")
-    meandot = torch.zeros(m * tiles * 80, dtype=torch.float64, device="cuda")
+    TN = 64
+    tiles = ((n_cand + TN - 1) // TN + 3) // 4 * 4
+    kq = torch.zeros(m * tiles * npad * 6 * TN, dtype=torch.uint8, device="cuda")
+    meandot = torch.zeros(m * tiles * TN, dtype=torch.float64, device="cuda")
     cand_dev = to_device(cand)
     _, pv = _lib.host_doubles(var0, m)
     _, pl = _lib.host_doubles(ls, m)
@@ -109,9 +110,9 @@ def main():
     for o in range(m):
         sq = ((x[:n, None, :] - cand[None, :, :]) ** 2).sum(-1)
         kt = np.exp(-0.5 * sq / ls[o] ** 2)  # (n, n_cand)
-        got = np.zeros((S, tiles * 80, npad), dtype=np.int64)
+        got = np.zeros((S, tiles * TN, npad), dtype=np.int64)
         for t in range(tiles):
-            got[:, t * 80:(t + 1) * 80, :] = planes_from_buffer(kqh[o, t], 80, nk)
+            got[:, t * TN:(t + 1) * TN, :] = planes_from_buffer(kqh[o, t], TN, nk)
         recon = sum(got[s].astype(np.float64) * 256.0 ** (S - 1 - s) for s in range(S)) * 2.0 ** -46
         err = np.abs(recon[:n_cand, :n].T - kt).max()
         print(f"[K* digits] obj {o}: max |recon - exp| = {err:.3e} (2^-47 = {2.0**-47:.3e}), "
@@ -121,19 +122,19 @@ def main():
 
     # ---- the MMA kernel against the exact integer contraction of the digits it was given
     for nsplit in sorted({1, min(2, nb), nb}):
-        q_dev = torch.zeros(m * nsplit * tiles * 80, dtype=torch.float64, device="cuda")
+        q_dev = torch.zeros(m * nsplit * tiles * TN, dtype=torch.float64, device="cuda")
         _lib.check(lib.bo_i8_sumsq(q_dev.data_ptr(), gp.wq.data_ptr(), gp.wscale.data_ptr(), kq.data_ptr(), n, m,
                                    n_cand, nsplit, pv, None))
         torch.cuda.synchronize()
-        qg = q_dev.cpu().numpy().reshape(m, nsplit, tiles * 80).sum(1)
+        qg = q_dev.cpu().numpy().reshape(m, nsplit, tiles * TN).sum(1)
         for o in range(m):
-            acc = [np.zeros((npad, tiles * 80), dtype=np.int64) for _ in range(S)]
+            acc = [np.zeros((npad, tiles * TN), dtype=np.int64) for _ in range(S)]
             for s in range(S):
                 for t in range(S - s):
                     acc[s + t] += Wd[o][s] @ Kd[o][t].T
-            b = [acc[2 * j] * 256 + acc[2 * j + 1] for j in range(3)]
-            v = (b[2].astype(np.float64) / 65536.0 + b[1].astype(np.float64)) / 65536.0 + b[0].astype(np.float64)
-            v = v * wsc[o][:, None]
+            b = [(acc[3 * j] * 256 + acc[3 * j + 1]) * 256 + acc[3 * j + 2] for j in range(2)]
+            f = wsc[o][:, None]
+            v = b[0].astype(np.float64) * f + b[1].astype(np.float64) * (f / 16777216.0)
             want = (v * v).sum(0) * var0[o] ** 2
             rel = np.abs(qg[o] - want).max() / max(np.abs(want).max(), 1e-300)
             print(f"[sumsq nsplit={nsplit}] obj {o}: max rel diff vs exact digit contraction = {rel:.3e}")
