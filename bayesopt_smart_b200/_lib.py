@@ -51,6 +51,7 @@ _SIGNATURES = {
     "bo_score_i8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                             c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             _dp, _dp, _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
+    "bo_i8_peak_tops": (c_int, [_dp, c_double, c_void_p]),
     "bo_i8_kstar_digits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, _dp, _dp, c_void_p]),
     "bo_i8_sumsq": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, _dp,

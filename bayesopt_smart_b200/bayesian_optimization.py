@@ -67,7 +67,7 @@ def _gather_shards(out, per_rank, n_total):
 def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, variance_objectives, std_mu_objectives,
              std_variance_objectives, ucb, acquisition_values, input_space, prior_mean, prior_variance,
              reference_point, n_evaluations, total_samples, n_objectives, function, betas, length_scales,
-             batch_size, bounds, callbacks=None, acquisition="sum_ucb"):
+             batch_size, bounds, callbacks=None, acquisition="sum_ucb", variance_engine=None):
     """The BO loop; same parameters and return value as the reference (:51-247).
 
     Each iteration: Powell fit of (length_scales, prior_variance) on the GPU log marginal likelihood,
@@ -86,7 +86,7 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
     equals the single-GPU one bit for bit.  The per-candidate host arrays are all-gathered when needed.
     """
     device = require_cuda()
-    gp = DeviceGP(device)
+    gp = DeviceGP(device, variance_engine=variance_engine)
     rank, world = bd.world_info()
     lo, hi = bd.shard_range(input_space.shape[0], world, rank)
     candidates = to_device(input_space[lo:hi], None, device)  # this rank's shard, uploaded once, stays in HBM
@@ -175,6 +175,7 @@ class BayesianOptimization:
         self.batch_size = kwargs.get("batch_size", cfg.DEFAULT_BATCH_SIZE)
         self.initial_samples = kwargs.get("initial_samples", cfg.DEFAULT_INITIAL_SAMPLES)
         self.acquisition = kwargs.get("acquisition", "sum_ucb")
+        self.variance_engine = kwargs.get("variance_engine")  # None: "dmma" (or BO_VARIANCE_ENGINE); "int8"
 
         # candidate set: every integer point of the box, upper bounds exclusive (:338-340)
         axes = np.meshgrid(*[np.arange(lo, hi) for lo, hi in bounds], indexing="ij")
@@ -207,7 +208,8 @@ class BayesianOptimization:
                     "prior_mean", "prior_variance", "reference_point", "n_evaluations", "total_samples",
                     "n_objectives", "function", "betas", "length_scales", "batch_size", "bounds")}
         self.x_vector, self.y_vector, self.n_evaluations = optimize(
-            **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition)
+            **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition,
+            variance_engine=self.variance_engine)
 
     def pareto_analysis(self) -> np.ndarray:
         """Pareto-efficient objective rows among the evaluated points (reference :465-488)."""

@@ -358,6 +358,11 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
                              alpha_dev, hp, min_variance, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
+int bo_i8_peak_tops(double* tops_host, double seconds, void* stream) {
+  BO_REQUIRE(tops_host && seconds > 0.0 && seconds < 5.0, "bad arguments");
+  return oz_peak_tops(tops_host, seconds, (cudaStream_t)stream);
+}
+
 int bo_i8_kstar_digits(uint8_t* kq_dev, double* meandot_dev, const void* cand_dev, int cand_kind, int ldc,
                        long long n_cand, const double* x_dev, int ldx, int n, int d, int m,
                        const double* alpha_dev, const double* prior_variance_host,

@@ -610,6 +610,58 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------- INT8 peak probe
+// The roofline denominator of oz_sumsq_kernel, measured on the chip like cuBLAS DGEMM is for the DMMA path: one
+// CTA per SM issues nothing but the kernel's own MMA batch (21 x tcgen05.mma.kind::i8 128x64x32, A from TMEM, B
+// from shared memory, 6 accumulators) back to back on resident operands -- no loads, no handshakes, no epilogue.
+__global__ void __launch_bounds__(64, 1) oz_peak_probe_kernel(int iters) {
+  __shared__ __align__(128) unsigned char sBp[OZ_B_STAGE];
+  __shared__ uint64_t done;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < OZ_B_STAGE; i += blockDim.x) sBp[i] = (unsigned char)((i * 2654435761u) >> 13);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)),
+                 "r"((uint32_t)OZ_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async proxy (MMA)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t b_lo = ((smem_u32(sBp) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t a_tm = tm + OZ_ASLOT_COL + (it & 1) * OZ_ASLOT_COLS;  // operand values are irrelevant
+#pragma unroll
+        for (int g = 0; g < OZ_PLANES; ++g) {
+#pragma unroll
+          for (int sp = 0; sp <= g; ++sp)
+            umma_i8_ts(tm + g * OZ_TN, a_tm + sp * (OZ_KS / 4), umma_desc_lo(b_lo + (g - sp) * (OZ_B_PLANE >> 4)),
+                       (it | sp) ? 1u : 0u);
+        }
+      }
+      umma_commit(&done);
+      mbar_wait(&done, 0);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)OZ_TMEM_COLS)
+                 : "memory");
+  }
+}
+
 template <typename CT, int D>
 int launch_oz_kstar_m(int m, dim3 grid, cudaStream_t st, unsigned char* kq, double* meandot, const CT* cand, int ldc,
                       long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk, const double* x,
@@ -757,6 +809,30 @@ int oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, const do
     case 2: return launch_oz_sumsq<2>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
     default: return launch_oz_sumsq<1>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
   }
+}
+
+int oz_peak_tops(double* tops, double seconds, cudaStream_t st) {
+  cudaEvent_t e0, e1;
+  BO_CUDA(cudaEventCreate(&e0));
+  BO_CUDA(cudaEventCreate(&e1));
+  const int sms = device_sm_count();
+  const double ops_per_iter = 21.0 * 2.0 * OZ_TM * OZ_TN * OZ_KS;
+  oz_peak_probe_kernel<<<sms, 64, 0, st>>>(200);  // warm-up
+  BO_LAUNCH_CHECK("oz_peak_probe_kernel");
+  // ~0.36 us per iteration at full clocks
+  int iters = (int)(seconds / 0.36e-6);
+  if (iters < 1000) iters = 1000;
+  BO_CUDA(cudaEventRecord(e0, st));
+  oz_peak_probe_kernel<<<sms, 64, 0, st>>>(iters);
+  BO_LAUNCH_CHECK("oz_peak_probe_kernel");
+  BO_CUDA(cudaEventRecord(e1, st));
+  BO_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  BO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tops = (double)sms * iters * ops_per_iter / (ms * 1e-3) / 1e12;
+  return BO_OK;
 }
 
 OzPlan make_oz_plan(int n, int m, long long n_cand) {

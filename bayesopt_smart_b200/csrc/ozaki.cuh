@@ -43,6 +43,9 @@ int oz_score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind
                         const double* wscale, const double* alpha, const ObjParams& hp, double min_variance,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// measured tcgen05.mma.kind::i8 rate of the kernel's own MMA batch on resident operands (TOP/s, mul + add)
+int oz_peak_tops(double* tops, double seconds, cudaStream_t st);
+
 // test hooks: the two halves of the pass on caller-provided buffers
 int oz_kstar_digits(unsigned char* kq, double* meandot, const void* cand, int cand_kind, int ldc, long long cand0,
                     long long n_cand, int tiles, int chunk_tiles, const double* x, int ldx, int n, int d, int m,

@@ -17,6 +17,12 @@ merged on device with the same total order.
 
 Printed keys follow the driver contract; `roofline` describes trmm_sumsq_kernel (FP64 DMMA bound),
 `cpu_baseline` the NumPy port of the reference (oracle/gp_oracle.py) on the host cores.
+
+The headline numbers (`value`, `e2e`, `roofline`) are measured with the FP64 DMMA variance engine, the
+one BASELINE.json's north star names.  The same step is then timed with the INT8 tensor-core engine
+(error-free digit splitting on tcgen05.mma.kind::i8, `variance_engine="int8"`) and reported under
+`int8_engine`, with its own roofline (executed against the kind::i8 rate measured in the same run) and
+the largest difference between the two engines' outputs on this workload.
 """
 from __future__ import annotations
 
@@ -226,12 +232,13 @@ def run_gpu_arm(args):
         gv, gi = bd.gather_topk(vals, idx)
         return bd.merge_topk(gp, gv, gi, vals.numel())
 
-    def step_resident():
+    def step_resident(g=None):
         """a1..a9 with every input already resident in HBM."""
-        gp.fit(x_dev, y_dev, mu0, var0, ls, n)
-        gp.score(cand_dev, betas, want=("acq",), out=out)
-        vals, idx = gp.topk(out["acq"], k + 16, index_base)
-        flags = gp.match_rows(idx, cand_dev, x_dev, index_base)
+        g = g or gp
+        g.fit(x_dev, y_dev, mu0, var0, ls, n)
+        g.score(cand_dev, betas, want=("acq",), out=out)
+        vals, idx = g.topk(out["acq"], k + 16, index_base)
+        flags = g.match_rows(idx, cand_dev, x_dev, index_base)
         vals = torch.where(flags.bool(), torch.full_like(vals, float("-inf")), vals)
         return exchange(vals, idx)
 
@@ -239,9 +246,9 @@ def run_gpu_arm(args):
     mirror = PinnedMirror()
     x_h, y_h, cand_h = (torch.from_numpy(a).pin_memory() for a in (x, y, cand))
 
-    def step_e2e():
+    def step_e2e(g=None):
         """Same step through the public host-buffer API: H2D of x, y, candidates; D2H of mu, var, acq, batch."""
-        res = hot_path_iteration(gp, x_h, y_h, cand_h, mu0, var0, ls, betas, n, k, mirror=mirror,
+        res = hot_path_iteration(g or gp, x_h, y_h, cand_h, mu0, var0, ls, betas, n, k, mirror=mirror,
                                  index_base=index_base)
         if world > 1:
             exchange(res["top_vals_dev"], res["top_idx_dev"])
@@ -322,6 +329,33 @@ def run_gpu_arm(args):
     h2d = x_h.numel() * 8 + y_h.numel() * 8 + cand_h.numel() * 8
     d2h = (2 * m + 1) * n_cand * 8 + (k + 16) * 16
 
+    # ---- the same step with the INT8 tensor-core variance engine (reported next to the headline, not as it)
+    i8 = None
+    if not args.profile_mode and not args.no_int8:
+        acq_dmma = out["acq"].clone()
+        top_dmma = step_resident()[1].clone()
+        gp8 = DeviceGP(dev, variance_engine="int8")
+        for _ in range(3):
+            step_resident(gp8)
+        lib.bo_launch_count(1)
+        lib.bo_profile_enable(1)
+        lib.bo_profile_read(None, None, None)
+        secs8, _ = timed_steps(lambda: step_resident(gp8), args.steps)
+        ms8, nl8, fl8 = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        lib.bo_profile_read(ctypes.byref(ms8), ctypes.byref(nl8), ctypes.byref(fl8))
+        lib.bo_profile_enable(0)
+        launches8 = int(lib.bo_launch_count(1))
+        top8 = step_resident(gp8)[1]
+        dacq = float((out["acq"] - acq_dmma).abs().max().item())
+        same_topk = bool(torch.equal(top8[:k], top_dmma[:k]))
+        for _ in range(2):
+            step_e2e(gp8)
+        secs8_e2e, _ = timed_steps(lambda: step_e2e(gp8), args.steps)
+        peak8 = ctypes.c_double()
+        _lib.check(lib.bo_i8_peak_tops(ctypes.byref(peak8), 0.03, None))
+        i8 = dict(secs=secs8, secs_e2e=secs8_e2e, ms=ms8.value, launches=int(nl8.value), flops=fl8.value,
+                  gpu_launches=launches8, dacq=dacq, same_topk=same_topk, peak_tops=peak8.value)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -368,6 +402,27 @@ def run_gpu_arm(args):
                      "algorithmic": "m*N^2 flop per candidate = 2.097e6; per launch x candidates in the chunk",
                      "launches": int(nl.value), "avg_launch_ms": ms.value / max(1, nl.value),
                      "share_of_step": ms.value * 1e-3 / secs},
+        "int8_engine": (None if i8 is None else {
+            "what": "same step with variance_engine='int8': |W k*|^2 by error-free splitting into 6 balanced "
+                    "base-256 digit planes, 21 digit-pair products on tcgen05.mma.kind::i8 (exact int32 in TMEM), "
+                    "int64/FP64 recombination; everything else identical",
+            "value": total_cands / i8["secs"], "unit": UNIT, "ms_per_step": 1e3 * i8["secs"] / args.steps,
+            "e2e": {"value": total_cands / i8["secs_e2e"], "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * i8["secs_e2e"] / args.steps},
+            "gpu_launches": i8["gpu_launches"],
+            "max_abs_acq_difference_vs_dmma": i8["dacq"], "same_top_batch_as_dmma": i8["same_topk"],
+            "roofline": {"kernel": "oz_sumsq_kernel", "bound": "tensor",
+                         "achieved": 21.0 * i8["flops"] / (i8["ms"] * 1e-3) / 1e12 if i8["ms"] > 0 else None,
+                         "peak": i8["peak_tops"], "unit": "TOP/s (int8 multiply + add)",
+                         "frac": (21.0 * i8["flops"] / (i8["ms"] * 1e-3) / 1e12 / i8["peak_tops"])
+                         if i8["ms"] > 0 and i8["peak_tops"] else None,
+                         "fp64_equivalent_tflops": i8["flops"] / (i8["ms"] * 1e-3) / 1e12 if i8["ms"] > 0 else None,
+                         "peak_source": "bo_i8_peak_tops: the kernel's own 21-MMA batch (kind::i8 128x64x32, A from "
+                                        "TMEM) on resident operands, one CTA per SM, ~30 ms, measured in this run "
+                                        "(MEASURED_PEAKS.json has no int8 entry; nominal B200 dense int8 4.5 POP/s)",
+                         "algorithmic": "21 digit-pair products x m*N^2 multiply-adds per candidate",
+                         "launches": i8["launches"], "avg_launch_ms": i8["ms"] / max(1, i8["launches"]),
+                         "share_of_step": i8["ms"] * 1e-3 / i8["secs"]}}),
         "cpu_baseline": ({"value": cpu_val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                           "sample": f"{cnt_cpu} of 10^6 grid candidates, one pass, NumPy/OpenBLAS port of the "
                                     "reference functions (oracle/gp_oracle.py)"} if cnt_cpu else None),
@@ -383,6 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-int8", action="store_true", help="skip the second measurement with the INT8 engine")
     ap.add_argument("--profile-mode", action="store_true",
                     help="short run for ncu: skips the DGEMM peak probe, the end-to-end leg and the CPU baseline")
     args = ap.parse_args()

@@ -130,6 +130,10 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
                 const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
                 const double* length_scales_host, const double* betas_host, double min_variance,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
+/* roofline denominator of the INT8 engine: the rate (TOP/s, multiply + add) at which this GPU executes the
+ * kernel's own MMA batch (tcgen05.mma.kind::i8 128x64x32, A from TMEM) on resident operands for about `seconds`
+ * seconds, one CTA per SM.  Synchronising.                                                              */
+int bo_i8_peak_tops(double* tops_host, double seconds, void* stream);
 /* test hooks: the two halves of the INT8 pass on caller-owned buffers (tiles = ceil(n_cand / 64) rounded up to a multiple of 4).
  *   kq_dev  : m * tiles * bo_npad(n) * 384 bytes of K* digit planes;  meandot_dev: (m, tiles*64) k*.alpha
  *   q_dev   : (m, nsplit, tiles*64) partial sums of |W k*|^2 (sum over nsplit = the full quadratic form)  */
