@@ -17,8 +17,8 @@
 // so one cp.async.bulk per operand per k-step fills a pipeline stage, and the smem descriptor is
 // (start, LBO = 128 B between the two k halves, SBO = 256 B between row groups).
 //
-// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warp 1: TMEM allocator + MMA issuer; warps
-// 2-9: epilogue, two warps per TMEM lane quarter with 32 columns each (tcgen05.ld, integer recombination in
+// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warps 1 and 10: TMEM allocator + the two
+// alternating MMA issuers; warps 2-9: A-operand feeders and epilogue, two warps per TMEM lane quarter with 32 columns each (tcgen05.ld, integer recombination in
 // triples, two exact int64 -> FP64 conversions, row scale, square, running per-thread sums over all row blocks
 // of the work unit; one transposed shuffle reduction per unit).
 // The W planes are the MMA's A operand and are read from TENSOR MEMORY: with A in shared memory a 128 x N x 32
@@ -39,14 +39,14 @@ namespace bo {
 namespace {
 
 constexpr int OZ_STAGES = 5;
-constexpr int OZ_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int OZ_THREADS = 352;  // producer warp, MMA warp, 8 feeder / epilogue warps, second MMA warp
 constexpr int OZ_EC = OZ_TN / 2;     // accumulator columns per epilogue warp
 constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 36864
 constexpr int OZ_ASLOT_COL = OZ_PLANES * OZ_TN;          // first TMEM column of the two A-operand slots
 constexpr int OZ_ASLOT_COLS = OZ_PLANES * (OZ_KS / 4);   // 48 columns: six planes of 128 lanes x 32 bytes
 constexpr int OZ_TMEM_COLS = 512;
 constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_TN * sizeof(double) +
-                           (2 * OZ_STAGES + 4) * sizeof(uint64_t) + 16;
+                           (2 * OZ_STAGES + 6) * sizeof(uint64_t) + 16;
 
 constexpr unsigned long long OZ_BIAS = 0x0000008080808080ull;  // 0x80 in each of the five low digit bytes
 constexpr double OZ_MAGIC = 6755399441055744.0;                // 1.5 * 2^52
@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * OZ_TN);
   uint64_t* empty = full + OZ_STAGES;
   uint64_t* a_ready = empty + OZ_STAGES;  // [2]: the A slot holds the planes of its k-step
-  uint64_t* tmem_full = a_ready + 2;
+  uint64_t* turn = a_ready + 2;  // [2]: issue token of the two MMA warps
+  uint64_t* tmem_full = turn + 2;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
@@ -413,6 +414,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     }
     mbar_init(&a_ready[0], 8);
     mbar_init(&a_ready[1], 8);
+    mbar_init(&turn[0], 1);
+    mbar_init(&turn[1], 1);
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 8);
     mbar_fence_init();
@@ -462,38 +465,53 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps the descriptors in
-    // uniform registers); one elected lane issues the MMAs and the commits.  Nothing but the a_ready wait, one
-    // fence and the commit sits between two batches of 21 MMAs: the tensor pipe buffers ~1 instruction, so every
-    // other instruction in this thread is a bubble (tools/umma_probe2.cu: try_wait 115, fence 48, commit 52 clk) =====
+  } else if (warp == 1 || warp == 10) {
+    // ===== two MMA issuers: warp 1 takes the even k-steps (A slot 0), warp 10 the odd ones (slot 1).  The
+    // tensor pipe buffers about one instruction, so whatever an issuing thread does between two batches (the
+    // a_ready wait, the fence, the commit: ~170 cycles) is a bubble -- unless the other issuer's batch is running
+    // meanwhile.  Issue order is serialised by a token: an issuer hands over after 17 of its 21 MMAs (the six
+    // that may overwrite, accumulate = 0 on the first k-step of a row block, come first), the pipe executes in
+    // issue order (verified exact over 400 alternating k-steps, tools/umma_probe3.cu), and integer accumulation
+    // commutes.  nk is a multiple of 4, so warp 1 always opens a row block and warp 10 always closes it.
+    // The whole warp walks the schedule (warp-uniform control flow keeps the descriptors in uniform registers);
+    // one elected lane issues. =====
+    const uint32_t me = warp == 1 ? 0u : 1u;
     int stage = 0;
-    uint32_t acc_phase = 0, g = 0;  // g: k-steps issued so far (A slot = g & 1)
+    uint32_t acc_phase = 0, g = 0;  // g: k-steps of the schedule so far
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    const uint32_t a_tm = tmem_base + OZ_ASLOT_COL + me * OZ_ASLOT_COLS;
     OzCursor c;
     for (oz_cursor_init(c, cluster_id, total_units, nsplit); c.valid;
          oz_cursor_next_block(c, n_clusters, total_units, nsplit, nb)) {
-      mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
+      if (me == 0) mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
       for (int ks = 0; ks < c.nk; ++ks, ++g) {
-        mbar_wait(&a_ready[g & 1], (g >> 1) & 1);  // feeders saw full[stage] and filled the A slot
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t b_lo = b_lo0 + stage * (OZ_B_STAGE >> 4);
-          const uint32_t first = ks > 0 ? 1u : 0u;
-          const uint32_t a_tm = tmem_base + OZ_ASLOT_COL + (g & 1) * OZ_ASLOT_COLS;
+        if ((g & 1u) == me) {
+          mbar_wait(&a_ready[me], (g >> 1) & 1);  // feeders saw full[stage] and filled this A slot
+          tc_fence_after();
+          if (g > 0) mbar_wait(&turn[me], ((g - 1) >> 1) & 1);  // the other issuer is 17 MMAs into k-step g-1
+          if (elect_one()) {
+            const uint32_t b_lo = b_lo0 + stage * (OZ_B_STAGE >> 4);
+            const uint32_t first = ks > 0 ? 1u : 0u;
 #pragma unroll
-          for (int gg = 0; gg < OZ_PLANES; ++gg) {
+            for (int gg = 0; gg < OZ_PLANES; ++gg)  // s = 0: the MMAs that start an accumulator
+              umma_i8_ts(tmem_base + gg * OZ_TN, a_tm, umma_desc_lo(b_lo + gg * (OZ_B_PLANE >> 4)), first);
+            int cnt = OZ_PLANES;
 #pragma unroll
-            for (int s = 0; s <= gg; ++s)
-              umma_i8_ts(tmem_base + gg * OZ_TN, a_tm + s * (OZ_KS / 4),
-                         umma_desc_lo(b_lo + (gg - s) * (OZ_B_PLANE >> 4)), s > 0 ? 1u : first);
+            for (int gg = 1; gg < OZ_PLANES; ++gg) {
+#pragma unroll
+              for (int sp = 1; sp <= gg; ++sp) {
+                umma_i8_ts(tmem_base + gg * OZ_TN, a_tm + sp * (OZ_KS / 4),
+                           umma_desc_lo(b_lo + (gg - sp) * (OZ_B_PLANE >> 4)), 1u);
+                if (++cnt == 17) mbar_arrive(&turn[me ^ 1u]);
+              }
+            }
+            // frees the smem stage (in every CTA of the cluster) and this A slot once these MMAs have read them
+            if (CL == 1) umma_commit(&empty[stage]);
+            else umma_commit_mc(&empty[stage], kMask);
+            if (ks == c.nk - 1) umma_commit(tmem_full);  // accumulators of this row block are complete
           }
-          // frees the smem stage (in every CTA of the cluster) and this A slot once the MMAs have read them
-          if (CL == 1) umma_commit(&empty[stage]);
-          else umma_commit_mc(&empty[stage], kMask);
-          if (ks == c.nk - 1) umma_commit(tmem_full);  // accumulators of this row block are complete
+          __syncwarp();
         }
-        __syncwarp();
         if (++stage == OZ_STAGES) stage = 0;
       }
       acc_phase ^= 1;

@@ -42,10 +42,10 @@ __device__ __forceinline__ void sttm8(uint32_t taddr, const uint32_t (&v)[8]) {
 }
 
 // mode 0: feeders + MMAs (the prototype); mode 1: same with test_wait polling; mode 2: MMAs only (no handshake)
-__global__ void __launch_bounds__(320, 1) probe(int mode, int iters, const unsigned char* gA, const unsigned char* gB, int* outD,
+__global__ void __launch_bounds__(352, 1) probe(int mode, int iters, const unsigned char* gA, const unsigned char* gB, int* outD,
                                                 unsigned long long* cyc) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t done, a_ready[2], slot_free[2];
+  __shared__ uint64_t done, done2, a_ready[2], slot_free[2], turn[2];
   __shared__ uint32_t slot;
   unsigned char* sA = smem;             // 6 planes x 4096 (canonical K-major image)
   unsigned char* sB = smem + 6 * 4096;  // 6 planes x 2048
@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(320, 1) probe(int mode, int iters, const unsig
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&done)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&done2)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&turn[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&turn[1])));
     for (int s = 0; s < 2; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&a_ready[s])));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&slot_free[s])));
@@ -72,31 +75,47 @@ __global__ void __launch_bounds__(320, 1) probe(int mode, int iters, const unsig
   const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | (8u << 24);
   const uint32_t b0 = smem_u32(sB);
   const uint32_t a_tm = tm + 6 * TN;
-  if (warp == 1) {
+  if (warp == 1 || (warp == 10 && mode == 3)) {
     uint32_t e;
     asm volatile("{\n.reg .pred px;\n.reg .b32 rx;\nelect.sync rx|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(e));
     if (e) {
+      const int me = warp == 1 ? 0 : 1;  // issuer 0: even k-steps (slot 0), issuer 1: odd k-steps (slot 1)
       const long long t0 = clock64();
-      for (int it = 0; it < iters; ++it) {
+      for (int it = (mode == 3 ? me : 0); it < iters; it += (mode == 3 ? 2 : 1)) {
         const int sl = it & 1;
         const uint32_t as = a_tm + sl * 48;
         if (mode != 2) {
           if (mode == 1) wait_bar<true>(&a_ready[sl], (it >> 1) & 1); else wait_bar<false>(&a_ready[sl], (it >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        if (mode == 3 && it > 0) wait_bar<false>(&turn[me], ((it - 1) >> 1) & 1);  // the other issuer handed over
+        if (mode == 3) {
+          // the six overwrite-capable MMAs (s = 0) first, the token after 17 of 21
+          int cnt = 0;
 #pragma unroll
-        for (int g = 0; g < 6; ++g)
+          for (int g = 0; g < 6; ++g) { umma_ts(tm + g * TN, as, desc_of(b0 + g * 2048), idesc, it ? 1u : 0u); ++cnt; }
 #pragma unroll
-          for (int s = 0; s <= g; ++s)
-            umma_ts(tm + g * TN, as + s * 8, desc_of(b0 + (g - s) * 2048), idesc, (it | s) ? 1u : 0u);
+          for (int g = 1; g < 6; ++g)
+#pragma unroll
+            for (int s = 1; s <= g; ++s) {
+              umma_ts(tm + g * TN, as + s * 8, desc_of(b0 + (g - s) * 2048), idesc, 1u);
+              if (++cnt == 17) arrive(&turn[me ^ 1]);
+            }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 6; ++g)
+#pragma unroll
+            for (int s = 0; s <= g; ++s)
+              umma_ts(tm + g * TN, as + s * 8, desc_of(b0 + (g - s) * 2048), idesc, (it | s) ? 1u : 0u);
+        }
         if (mode != 2) commit(&slot_free[sl]);
       }
-      commit(&done);
-      wait_bar<false>(&done, 0);
-      cyc[blockIdx.x] = (unsigned long long)(clock64() - t0);
+      commit(me ? &done2 : &done);
+      wait_bar<false>(me ? &done2 : &done, 0);
+      if (me == 0) cyc[blockIdx.x] = (unsigned long long)(clock64() - t0);
     }
     __syncwarp();
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 10) {
     // feeders: quarter = warp % 4 (TMEM lanes), half = (warp - 2) / 4 (planes 3*half .. 3*half + 2)
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
@@ -163,9 +182,11 @@ int main() {
   cudaMalloc(&dA, sizeof(imgA)); cudaMalloc(&dB, sizeof(imgB)); cudaMalloc(&dD, 128 * 6 * TN * 4); cudaMalloc(&dC, 8 * sms);
   cudaMemcpy(dA, imgA, sizeof(imgA), cudaMemcpyHostToDevice); cudaMemcpy(dB, imgB, sizeof(imgB), cudaMemcpyHostToDevice);
   // ---- exactness: 7 k-steps with the handshake
-  const int vit = 7;
-  probe<<<1, 320, smem>>>(0, vit, dA, dB, dD, dC);
-  cudaError_t err = cudaDeviceSynchronize();
+  cudaError_t err;
+  for (int vmode : {0, 3}) {
+  const int vit = vmode == 3 ? 400 : 7;
+  probe<<<1, 352, smem>>>(vmode, vit, dA, dB, dD, dC);
+  err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("CUDA error in verify: %s\n", cudaGetErrorString(err)); return 1; }
   static int hD[128 * 6 * TN];
   cudaMemcpy(hD, dD, sizeof(hD), cudaMemcpyDeviceToHost);
@@ -175,15 +196,16 @@ int main() {
     for (int s = 0; s <= g; ++s) for (int k = 0; k < 32; ++k) want += (long)A[s][i][k] * (long)B[g - s][j][k];
     bad += hD[i * 6 * TN + g * TN + j] != (int)(want * vit);
   }
-  printf("{\"verify\": \"lds + tcgen05.st feeders + TS mma, %d k-steps\", \"mismatch\": %ld, \"of\": %d}\n", vit, bad, 128 * 6 * TN);
+  printf("{\"verify\": \"lds + tcgen05.st feeders + TS mma, %d k-steps, %s\", \"mismatch\": %ld, \"of\": %d}\n", vit, vmode == 3 ? "two issuers" : "one issuer", bad, 128 * 6 * TN);
+  }
   // ---- timing
   unsigned long long* h = (unsigned long long*)malloc(8 * sms);
   const int iters = 4000;
-  for (int mode : {0, 1, 2}) {
+  for (int mode : {0, 3, 2}) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    probe<<<sms, 320, smem>>>(mode, 100, dA, dB, nullptr, dC);
+    probe<<<sms, 352, smem>>>(mode, 100, dA, dB, nullptr, dC);
     cudaEventRecord(e0);
-    probe<<<sms, 320, smem>>>(mode, iters, dA, dB, nullptr, dC);
+    probe<<<sms, 352, smem>>>(mode, iters, dA, dB, nullptr, dC);
     cudaEventRecord(e1);
     err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("CUDA error: %s (mode=%d)\n", cudaGetErrorString(err), mode); return 1; }
@@ -191,7 +213,7 @@ int main() {
     cudaMemcpy(h, dC, 8 * sms, cudaMemcpyDeviceToHost);
     double c = 0; for (int i = 0; i < sms; ++i) c += (double)h[i]; c /= sms;
     printf("{\"mode\": \"%s\", \"clk_per_kstep\": %.1f, \"ideal\": 672, \"ms\": %.3f}\n",
-           mode == 0 ? "feeders+mma, try_wait" : mode == 1 ? "feeders+mma, test_wait" : "mma only", c / iters, ms);
+           mode == 0 ? "feeders+mma, one issuer" : mode == 3 ? "feeders+mma, two issuers alternating" : "mma only", c / iters, ms);
   }
   return 0;
 }
