@@ -2,6 +2,7 @@
 
     torchrun --nproc-per-node 8 tools/run_sharded_config.py cfg3     # ZDT2 d=10, N=4096, 16 M candidates
     torchrun --nproc-per-node 8 tools/run_sharded_config.py cfg4     # DTLZ2 d=8, N=2048, m=3, 8 M candidates + Pareto
+    torchrun --nproc-per-node 8 tools/run_sharded_config.py hl int8  # N=4096, d=6, 16 M candidates, INT8 engine
 
 Candidates are generated on the device per shard from a generator seeded by the global chunk index, so any rank
 count produces the same global candidate set.  Timing: CUDA events per rank, MAX over ranks."""
@@ -23,7 +24,9 @@ from oracle import gp_oracle as orc  # noqa: E402
 
 CONFIGS = {"cfg3": dict(fn="zdt2", n=4096, d=10, m=2, ls=0.5, total=16_000_000, pareto=False),
            "cfg4": dict(fn="dtlz2", n=2048, d=8, m=3, ls=0.5, total=8_000_000, pareto=True),
-           "cfg2x": dict(fn="zdt1", n=1024, d=6, m=2, ls=0.3, total=8_000_000, pareto=False)}
+           "cfg2x": dict(fn="zdt1", n=1024, d=6, m=2, ls=0.3, total=8_000_000, pareto=False),
+           # the north star's headline shape: N=4096, d=6, 2 objectives
+           "hl": dict(fn="zdt1", n=4096, d=6, m=2, ls=0.3, total=16_000_000, pareto=False)}
 CHUNK = 250_000  # candidates per generator chunk (global chunk index = seed)
 
 
@@ -39,6 +42,7 @@ def shard_candidates(lo, hi, d, dev):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+    engine = sys.argv[2] if len(sys.argv) > 2 else "dmma"  # variance engine: dmma | int8
     cfg = CONFIGS[tag]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -53,7 +57,7 @@ def main():
     ls, betas = np.full(m, cfg["ls"]), np.full(m, 2.0)
     lo, hi = bd.shard_range(cfg["total"], world, rank)
     cand = shard_candidates(lo, hi, d, dev)
-    gp = DeviceGP(dev)
+    gp = DeviceGP(dev, variance_engine=engine)
     xd, yd = to_device(x, device=dev), to_device(y, device=dev)
     want = ("acq", "ucb") if cfg["pareto"] else ("acq",)
     out = {k: torch.empty((hi - lo,) if k == "acq" else (m, hi - lo), dtype=torch.float64, device=dev) for k in want}
@@ -90,7 +94,7 @@ def main():
     if rank == 0:
         best = min(times)
         flops = float(cfg["total"]) * m * n * n
-        print(json.dumps({"config": tag, "n_gpus": world, "n_train": n, "dims": d, "objectives": m,
+        print(json.dumps({"config": tag, "variance_engine": engine, "n_gpus": world, "n_train": n, "dims": d, "objectives": m,
                           "candidates_total": cfg["total"], "step_s": best, "cand_per_s": cfg["total"] / best,
                           "algorithmic_tflops_total": flops / best / 1e12,
                           "algorithmic_tflops_per_gpu": flops / best / 1e12 / world,
