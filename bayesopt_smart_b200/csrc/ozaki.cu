@@ -152,15 +152,22 @@ __global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long stri
 // six 16-byte plane rows; the posterior-mean dot product k*.alpha is accumulated from the unquantised values.
 constexpr int OZK_ROWS = 256;
 constexpr int OZK_THREADS = 2 * OZ_TN;
+#ifndef OZK_MIN_CTAS
+#define OZK_MIN_CTAS 3
+#endif
+// row of the staged training block: D coordinates (D is even) then MOBJ alphas, padded to whole 16-byte pairs --
+// every lane of a warp reads the same row (broadcast), so the rows can be read with 16-byte loads
+__host__ __device__ constexpr int ozk_row_doubles(int d, int m) { return (d + m + 1) & ~1; }
 
 template <typename CT, int D, int MOBJ>
-__global__ void __launch_bounds__(OZK_THREADS, 2)
+__global__ void __launch_bounds__(OZK_THREADS, OZK_MIN_CTAS)
     oz_kstar_digits_kernel(unsigned char* __restrict__ kq, double* __restrict__ meandot, const CT* __restrict__ cand,
                            int ldc, long long cand0, long long n_cand, int chunk_tiles, long long ld_chunk,
                            const double* __restrict__ x, int ldx, int n, int npad, int d,
                            const double* __restrict__ alpha, int alpha_ld, ObjParams hp) {
   __shared__ double exp_tab[64];
-  __shared__ double xs[OZK_ROWS][(D + MOBJ) | 1];
+  constexpr int RS = ozk_row_doubles(D, MOBJ);
+  __shared__ __align__(16) double xs[OZK_ROWS][RS];
   __shared__ double mred[MOBJ][OZ_TN];
   const int tid = threadIdx.x;
   if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
@@ -187,16 +194,29 @@ __global__ void __launch_bounds__(OZK_THREADS, 2)
 
   for (int r0 = 0; r0 < npad; r0 += OZK_ROWS) {
     __syncthreads();
-    for (int e = tid; e < OZK_ROWS * (D + MOBJ); e += OZK_THREADS) {
-      const int rr = e / (D + MOBJ), k = e - rr * (D + MOBJ);
-      const int row = r0 + rr;
-      double v = 0.0;
-      if (row < npad) {
-        const int rc = row < n ? row : n - 1;  // padded rows reuse the last real point (finite values)
-        if (k < D) v = (k < d) ? x[(long long)rc * ldx + k] : 0.0;
-        else v = (row < n) ? alpha[(long long)(k - D) * alpha_ld + row] : 0.0;
+    {
+      // all loads of this thread first, then the stores: the trip count is a compile-time constant, so the global
+      // loads are in flight together instead of one load -> store round trip per element
+      constexpr int PER_THREAD = OZK_ROWS * RS / OZK_THREADS;
+      double stage[PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        const int e = tid + i * OZK_THREADS;
+        const int rr = e / RS, k = e - rr * RS;
+        const int row = r0 + rr;
+        double v = 0.0;
+        if (row < npad) {
+          const int rc = row < n ? row : n - 1;  // padded rows reuse the last real point (finite values)
+          if (k < D) v = (k < d) ? x[(long long)rc * ldx + k] : 0.0;
+          else if (k < D + MOBJ) v = (row < n) ? alpha[(long long)(k - D) * alpha_ld + row] : 0.0;
+        }
+        stage[i] = v;
       }
-      xs[rr][k] = v;
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        const int e = tid + i * OZK_THREADS;
+        xs[e / RS][e % RS] = stage[i];
+      }
     }
     __syncthreads();
     const int ks_end = min(nk_tot, (r0 + OZK_ROWS) / OZ_KS);
@@ -205,12 +225,14 @@ __global__ void __launch_bounds__(OZK_THREADS, 2)
       double sq[16];
 #pragma unroll
       for (int b = 0; b < 16; ++b) {
-        const double* xr = xs[kb + b];
+        const double2* xr = reinterpret_cast<const double2*>(xs[kb + b]);
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          const double df = xr[k] - cc[k];
-          s = fma(df, df, s);
+        for (int k = 0; k < D; k += 2) {  // same order of accumulation as the scalar loop: k = 0..D-1
+          const double2 xv = xr[k >> 1];
+          const double d0 = xv.x - cc[k], d1 = xv.y - cc[k + 1];
+          s = fma(d0, d0, s);
+          s = fma(d1, d1, s);
         }
         sq[b] = s;
       }
@@ -315,31 +337,6 @@ __device__ __forceinline__ double triple_to_double(int a, int b, int c) {
   return __longlong_as_double(v + 0x4338000000000000ll) - OZ_MAGIC;
 }
 
-// multicast variants for a cluster of CTAs that walk the same W row blocks on different candidate tiles
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                            uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], "
-      "%4;" ::"r"(smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // row blocks of one candidate tile are dealt to `nsplit` CTAs in serpentine order (equal k-step totals +-1 block)
 __device__ __forceinline__ int oz_row_block(int t, int r, int nsplit) {
   return t * nsplit + ((t & 1) ? (nsplit - 1 - r) : r);
@@ -383,11 +380,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& lo, const 
                : "memory");
 }
 
-// CL = CTAs per cluster.  The CTAs of a cluster take CL consecutive candidate tiles of the same (objective, row
-// split): they need the same W k-steps at the same time, so each CTA fetches 1/CL of every W stage and
-// multicasts it into all CL shared memories.  (Measured: no gain on B200 -- the pass is not L2-bound -- so the
-// default is CL = 1; BO_I8_CLUSTER=2|4 selects the multicast variants.)
-template <int CL>
+// (A variant in which clusters of 2 or 4 CTAs multicast the W stages into each other's shared memory was measured:
+// no gain -- the pass is not L2-bound -- and 4-CTA clusters lose SMs to GPC fragmentation.  It is not kept.)
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const unsigned char* __restrict__ wq,
                     long long strideWq, const double* __restrict__ wscale, const unsigned char* __restrict__ kq,
@@ -410,7 +404,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);  // one commit from the MMA warp of every CTA in the cluster
+      mbar_init(&empty[s], 1);
     }
     mbar_init(&a_ready[0], 8);
     mbar_init(&a_ready[1], 8);
@@ -428,12 +422,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer copies into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int crank = CL > 1 ? (int)cluster_rank() : 0;
-  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+  const int first_unit = blockIdx.x, unit_stride = gridDim.x;
 
   if (warp == 0) {
     // ===== producer: one lane streams k-step stages with the bulk-copy engine =====
@@ -441,22 +432,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       OzCursor c;
-      for (oz_cursor_init(c, cluster_id, total_units, nsplit); c.valid;
-           oz_cursor_next_block(c, n_clusters, total_units, nsplit, nb)) {
+      for (oz_cursor_init(c, first_unit, total_units, nsplit); c.valid;
+           oz_cursor_next_block(c, unit_stride, total_units, nsplit, nb)) {
         const int o = (c.u / nsplit) % m;
-        const int ct = (c.u / (nsplit * m)) * CL + crank;
+        const int ct = c.u / (nsplit * m);
         const unsigned char* At = wq + (long long)o * strideWq + 2LL * c.ib * (c.ib + 1) * OZ_A_STAGE;
         const unsigned char* Ko = kq + ((long long)o * chunk_tiles + ct) * nk_tot * OZ_B_STAGE;
         for (int ks = 0; ks < c.nk; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
-          if (CL == 1) {
-            bulk_g2s(sA + stage * OZ_A_STAGE, At + (long long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
-          } else {
-            constexpr int kSlice = OZ_A_STAGE / CL;
-            bulk_g2s_mc(sA + stage * OZ_A_STAGE + crank * kSlice, At + (long long)ks * OZ_A_STAGE + crank * kSlice,
-                        kSlice, &full[stage], kMask);
-          }
+          bulk_g2s(sA + stage * OZ_A_STAGE, At + (long long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
           bulk_g2s(sB + stage * OZ_B_STAGE, Ko + (long long)ks * OZ_B_STAGE, OZ_B_STAGE, &full[stage]);
           if (++stage == OZ_STAGES) {
             stage = 0;
@@ -481,8 +466,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
     const uint32_t a_tm = tmem_base + OZ_ASLOT_COL + me * OZ_ASLOT_COLS;
     OzCursor c;
-    for (oz_cursor_init(c, cluster_id, total_units, nsplit); c.valid;
-         oz_cursor_next_block(c, n_clusters, total_units, nsplit, nb)) {
+    for (oz_cursor_init(c, first_unit, total_units, nsplit); c.valid;
+         oz_cursor_next_block(c, unit_stride, total_units, nsplit, nb)) {
       if (me == 0) mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
       for (int ks = 0; ks < c.nk; ++ks, ++g) {
         if ((g & 1u) == me) {
@@ -505,9 +490,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 if (++cnt == 17) mbar_arrive(&turn[me ^ 1u]);
               }
             }
-            // frees the smem stage (in every CTA of the cluster) and this A slot once these MMAs have read them
-            if (CL == 1) umma_commit(&empty[stage]);
-            else umma_commit_mc(&empty[stage], kMask);
+            umma_commit(&empty[stage]);  // frees the smem stage and this A slot once these MMAs have read them
             if (ks == c.nk - 1) umma_commit(tmem_full);  // accumulators of this row block are complete
           }
           __syncwarp();
@@ -530,8 +513,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     uint32_t fed = 0;        // k-steps fed so far (global count: stage = fed % STAGES, slot = fed & 1)
     uint32_t drain_end = 0;  // global index one past the last k-step of the row block being drained
     OzCursor fc, dc;         // feeding runs up to two k-steps ahead of draining
-    oz_cursor_init(fc, cluster_id, total_units, nsplit);
-    oz_cursor_init(dc, cluster_id, total_units, nsplit);
+    oz_cursor_init(fc, first_unit, total_units, nsplit);
+    oz_cursor_init(dc, first_unit, total_units, nsplit);
     double ssum[OZ_EC];
 #pragma unroll
     for (int c = 0; c < OZ_EC; ++c) ssum[c] = 0.0;
@@ -560,12 +543,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[fed & 1]);
         ++fed;
-        if (++fc.ks == fc.nk) oz_cursor_next_block(fc, n_clusters, total_units, nsplit, nb);
+        if (++fc.ks == fc.nk) oz_cursor_next_block(fc, unit_stride, total_units, nsplit, nb);
       }
       // ---- drain the accumulators of row block dc
       const int r = dc.u % nsplit;
       const int o = (dc.u / nsplit) % m;
-      const int ct = (dc.u / (nsplit * m)) * CL + crank;
+      const int ct = dc.u / (nsplit * m);
       const double f = wscale[(long long)o * npad + dc.ib * OZ_TM + row];
       const double f24 = f * (1.0 / 16777216.0);
       mbar_wait(tmem_full, acc_phase);
@@ -589,7 +572,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
       acc_phase ^= 1;
-      const bool unit_done = oz_cursor_next_block(dc, n_clusters, total_units, nsplit, nb);
+      const bool unit_done = oz_cursor_next_block(dc, unit_stride, total_units, nsplit, nb);
       if (unit_done) {
         // sum over the 32 rows of this warp: transposed butterfly, 32 -> 16 -> 8 -> 4 -> 2 -> 1 values per lane;
         // lane L ends up with the sum of column half*32 + L
@@ -619,7 +602,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still write its shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -750,83 +732,22 @@ int oz_kstar_digits(unsigned char* kq, double* meandot, const void* cand, int ca
                                  n_cand, chunk_tiles, ld_chunk, x, ldx, n, npad, alpha, npad, hp);
 }
 
-namespace {
-
-int oz_cluster_size() {
-  static const int cl = [] {
-    const char* e = getenv("BO_I8_CLUSTER");
-    const int v = e ? atoi(e) : 1;
-    return (v == 1 || v == 2 || v == 4) ? v : 1;
-  }();
-  return cl;
-}
-
-template <int CL>
-int launch_oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, long long strideWq,
-                    const double* wscale, const unsigned char* kq, int npad, int nb, int chunk_tiles, int nsplit,
-                    int m, int tiles, const ObjParams& hp, cudaStream_t st) {
-  static bool attr_set = false;
-  static int max_clusters = 0;
-  if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    max_clusters = device_sm_count() / CL;
-    if (CL > 1) {
-      // how many clusters of CL one-CTA-per-SM blocks the GPCs can hold at once
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(device_sm_count() / CL * CL);
-      q.blockDim = dim3(OZ_THREADS);
-      q.dynamicSmemBytes = OZ_SMEM;
-      cudaLaunchAttribute a[1];
-      a[0].id = cudaLaunchAttributeClusterDimension;
-      a[0].val.clusterDim.x = CL;
-      a[0].val.clusterDim.y = 1;
-      a[0].val.clusterDim.z = 1;
-      q.attrs = a;
-      q.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, oz_sumsq_kernel<CL>, &q) == cudaSuccess && nc > 0) max_clusters = nc;
-      cudaGetLastError();
-    }
-    attr_set = true;
-  }
-  const int groups = (tiles + CL - 1) / CL;
-  const int units = groups * m * nsplit;
-  const int clusters = units < max_clusters ? units : max_clusters;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CL));
-  cfg.blockDim = dim3(OZ_THREADS);
-  cfg.dynamicSmemBytes = OZ_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  BO_CUDA(cudaLaunchKernelEx(&cfg, oz_sumsq_kernel<CL>, part, ld_chunk, wq, strideWq, wscale, kq, npad, nb,
-                             npad / OZ_KS, chunk_tiles, nsplit, m, units, hp));
-  BO_LAUNCH_CHECK("oz_sumsq_kernel");
-  return BO_OK;
-}
-
-}  // namespace
-
-// `chunk_tiles` (the K* / part allocation) must be a multiple of the cluster size: a cluster always walks CL
-// tiles, the ones beyond `tiles` read allocated-but-unwritten digits and their sums are never used.
 int oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, const double* wscale,
              const unsigned char* kq, int n, int m, int tiles, int chunk_tiles, int nsplit, const ObjParams& hp,
              cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    attr_set = true;
+  }
   const int npad = round_up(n, OZ_TM), nb = npad / OZ_TM;
   if (nsplit > nb) nsplit = nb;
-  int cl = oz_cluster_size();
-  while (cl > 1 && chunk_tiles % cl != 0) cl >>= 1;
-  const long long strideWq = (long long)oz_wq_bytes(n);
-  switch (cl) {
-    case 4: return launch_oz_sumsq<4>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
-    case 2: return launch_oz_sumsq<2>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
-    default: return launch_oz_sumsq<1>(part, ld_chunk, wq, strideWq, wscale, kq, npad, nb, chunk_tiles, nsplit, m, tiles, hp, st);
-  }
+  const int units = tiles * m * nsplit;
+  const unsigned grid = (unsigned)(units < device_sm_count() ? units : device_sm_count());
+  oz_sumsq_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(part, ld_chunk, wq, (long long)oz_wq_bytes(n), wscale, kq, npad,
+                                                     nb, npad / OZ_KS, chunk_tiles, nsplit, m, units, hp);
+  BO_LAUNCH_CHECK("oz_sumsq_kernel");
+  return BO_OK;
 }
 
 int oz_peak_tops(double* tops, double seconds, cudaStream_t st) {
@@ -871,7 +792,6 @@ OzPlan make_oz_plan(int n, int m, long long n_cand) {
   if (ct > cap) ct = cap < 1 ? 1 : cap;
   if (ct > tiles) ct = tiles;
   if (ct < 1) ct = 1;
-  ct = (ct + 3) / 4 * 4;  // whole clusters of candidate tiles (oz_sumsq)
   p.chunk_tiles = (int)ct;
   p.ld_chunk = ct * OZ_TN;
   p.nbuf = 1;
