@@ -220,7 +220,7 @@ def run_gpu_arm(args):
     n_cand = cand.shape[0]
     index_base = rank * n_cand
 
-    gp = DeviceGP(dev)
+    gp = DeviceGP(dev, variance_engine=args.engine)
     x_dev, y_dev, cand_dev = to_device(x, device=dev), to_device(y, device=dev), to_device(cand, device=dev)
     out = {"acq": torch.empty(n_cand, dtype=torch.float64, device=dev)}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -297,6 +297,13 @@ def run_gpu_arm(args):
         return 2.0 * nn**3 / best / 1e12
 
     peak_tflops = dgemm_peak() if (rank == 0 and not args.profile_mode) else 0.0
+    peak_i8_tops = 0.0
+    if args.engine == "int8" and rank == 0 and not args.profile_mode:
+        import ctypes as _ct
+
+        pk = _ct.c_double()
+        _lib.check(lib.bo_i8_peak_tops(_ct.byref(pk), 0.03, None))
+        peak_i8_tops = pk.value
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -331,7 +338,7 @@ def run_gpu_arm(args):
 
     # ---- the same step with the INT8 tensor-core variance engine (reported next to the headline, not as it)
     i8 = None
-    if not args.profile_mode and not args.no_int8:
+    if not args.profile_mode and not args.no_int8 and args.engine == "dmma":
         acq_dmma = out["acq"].clone()
         top_dmma = step_resident()[1].clone()
         gp8 = DeviceGP(dev, variance_engine="int8")
@@ -361,15 +368,19 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    traffic = None
-    try:  # DRAM bytes per launch from the committed ncu capture of the same kernel / workload
-        with open(os.path.join(ROOT, "profiles", "trmm_traffic.json")) as f:
-            tr = json.load(f)
-        if tr["n_train"] == n and tr["objectives"] == m:
-            traffic = {"bytes_per_launch": tr["dram_bytes_per_launch"],
-                       "candidates_per_launch": tr["candidates_per_launch"], "source": "profiles/trmm_traffic.json"}
-    except (OSError, KeyError, ValueError):
-        pass
+    def load_traffic(name):
+        """DRAM bytes per launch from the committed ncu capture of the same kernel / workload"""
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)
+            if tr["n_train"] == n and tr["objectives"] == m:
+                return {"bytes_per_launch": tr["dram_bytes_per_launch"],
+                        "candidates_per_launch": tr["candidates_per_launch"], "source": "profiles/" + name}
+        except (OSError, KeyError, ValueError):
+            pass
+        return None
+
+    traffic = load_traffic("trmm_traffic.json" if args.engine == "dmma" else "oz_traffic.json")
     total_cands = n_cand * world * args.steps
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
     # bounded CPU sample of the same workload (reference port), ~10-20 s
@@ -382,7 +393,7 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": total_cands / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "variance_engine": args.engine,
         "config": {"workload": w["name"], "n_train": n, "dims": w["d"], "objectives": m,
                    "candidates_per_gpu": n_cand, "batch_size": k, "length_scale": w["ls"], "beta": w["beta"],
                    "step": "update_k+invert_k (Cholesky/W) + K* + mean + variance + standardise + UCB + sum-UCB "
@@ -395,13 +406,22 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * secs_e2e / args.steps,
                 "api": "engine.hot_path_iteration (pinned host x, y, input_space in; mu, var, acq, batch out)"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "trmm_sumsq_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tflops,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None, "traffic": traffic,
-                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is absent from "
-                                    "MEASURED_PEAKS.json; nominal B200 FP64 tensor 37-40 TFLOP/s)",
-                     "algorithmic": "m*N^2 flop per candidate = 2.097e6; per launch x candidates in the chunk",
-                     "launches": int(nl.value), "avg_launch_ms": ms.value / max(1, nl.value),
-                     "share_of_step": ms.value * 1e-3 / secs},
+        "roofline": ({"kernel": "trmm_sumsq_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tflops,
+                      "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None, "traffic": traffic,
+                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is absent from "
+                                     "MEASURED_PEAKS.json; nominal B200 FP64 tensor 37-40 TFLOP/s)",
+                      "algorithmic": "m*N^2 flop per candidate = 2.097e6; per launch x candidates in the chunk",
+                      "launches": int(nl.value), "avg_launch_ms": ms.value / max(1, nl.value),
+                      "share_of_step": ms.value * 1e-3 / secs} if args.engine == "dmma" else
+                     {"kernel": "oz_sumsq_kernel", "bound": "tensor", "achieved": 21.0 * achieved,
+                      "peak": peak_i8_tops, "unit": "TOP/s (int8 multiply + add)",
+                      "frac": 21.0 * achieved / peak_i8_tops if peak_i8_tops else None, "traffic": traffic,
+                      "fp64_equivalent_tflops": achieved,
+                      "peak_source": "bo_i8_peak_tops: the kernel's own 21-MMA batch on resident operands, one CTA "
+                                     "per SM, ~30 ms, measured in this run",
+                      "algorithmic": "21 digit-pair products x m*N^2 multiply-adds per candidate",
+                      "launches": int(nl.value), "avg_launch_ms": ms.value / max(1, nl.value),
+                      "share_of_step": ms.value * 1e-3 / secs}),
         "int8_engine": (None if i8 is None else {
             "what": "same step with variance_engine='int8': |W k*|^2 by error-free splitting into 6 balanced "
                     "base-256 digit planes, 21 digit-pair products on tcgen05.mma.kind::i8 (exact int32 in TMEM), "
@@ -421,6 +441,7 @@ def run_gpu_arm(args):
                                         "TMEM) on resident operands, one CTA per SM, ~30 ms, measured in this run "
                                         "(MEASURED_PEAKS.json has no int8 entry; nominal B200 dense int8 4.5 POP/s)",
                          "algorithmic": "21 digit-pair products x m*N^2 multiply-adds per candidate",
+                         "traffic": load_traffic("oz_traffic.json"),
                          "launches": i8["launches"], "avg_launch_ms": i8["ms"] / max(1, i8["launches"]),
                          "share_of_step": i8["ms"] * 1e-3 / i8["secs"]}}),
         "cpu_baseline": ({"value": cpu_val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
@@ -439,6 +460,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-int8", action="store_true", help="skip the second measurement with the INT8 engine")
+    ap.add_argument("--engine", default="dmma", choices=["dmma", "int8"],
+                    help="variance engine of the headline measurement (default: the FP64 DMMA engine; with int8 the "
+                         "whole line, roofline included, describes the INT8 engine)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="short run for ncu: skips the DGEMM peak probe, the end-to-end leg and the CPU baseline")
     args = ap.parse_args()
