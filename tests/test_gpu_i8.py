@@ -220,3 +220,19 @@ def test_optimize_runs_with_the_int8_engine(env):
     assert np.isfinite(bo.y_vector[: 8 + 9]).all()
     assert is_pareto_efficient(bo.y_vector[: 8 + 9]).any()
     assert bo.variance_objectives.shape[1] == 900 and (bo.variance_objectives >= 1e-10).all()
+
+
+def test_parity_edge_and_full_size_suites_pass_with_the_int8_engine_as_default(env):
+    """Every other GPU test file (golden / oracle parity, edge shapes, BASELINE-size properties, the 2-rank loop)
+    re-run with BO_VARIANCE_ENGINE=int8, i.e. with the INT8 engine behind every DeviceGP() of those tests."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join("tests", f) for f in ("test_gpu_parity.py", "test_gpu_edges.py", "test_gpu_full_size.py",
+                                                "test_gpu_multi.py")]
+    env2 = dict(os.environ, BO_VARIANCE_ENGINE="int8")
+    r = subprocess.run([sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x"], cwd=root, env=env2,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
