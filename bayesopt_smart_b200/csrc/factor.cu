@@ -3,8 +3,8 @@
 // identity block in the padding, so every GEMM below runs on whole tiles.
 //
 //   gram_kernel        K = var * exp(-0.5 |xi-xj|^2 / ls^2) (+ diag_add), identity padding
-//   potf2_kernel       64x64 diagonal block: in-shared-memory Cholesky, one barrier per column
-//   trsm_panel_kernel  panel <- panel * L_jj^-T by substitution (backward stable, like dtrsm)
+//   potf2_kernel       64x64 diagonal block: one row per thread in registers, column broadcast through smem
+//   trsm_panel_kernel  panel <- panel * L_jj^-T by substitution (backward stable, like dtrsm), row per thread
 //   block_inverse      inverses of all diagonal blocks in parallel (base of W = L^-1 and of the MLL solve)
 //   cholesky_blocked   right-looking: potf2 -> panel TRSM -> trailing SYRK (DMMA)
 //   tri_inverse        W = L^-1 by recursive doubling: W21 = -W22 (L21 W11), two batched GEMMs per level
@@ -52,58 +52,78 @@ __global__ void gram_kernel(double* __restrict__ K, long long ldk, long long str
 }
 
 // ----------------------------------------------------------------------------------------- potf2
-// One CTA per matrix in the batch: lower Cholesky factor of the 64x64 diagonal block in shared memory,
-// ONE barrier per column: the trailing update reads the unscaled column j of S and the pivot, the scaled
-// column goes to a second array (nobody reads column j of S again).
+// One CTA (64 threads) per matrix in the batch: lower Cholesky factor of the 64x64 diagonal block.
 //
 // Pivot policy (pol[2b] = floor, pol[2b+1] = negative tolerance): in exact arithmetic every pivot of
 // K + jitter*I is >= jitter, so a pivot that rounding pushed below the floor -- but not below -tolerance --
 // is clamped to the floor (counted in info[batch + b]); a pivot below -tolerance or NaN means the input is
 // genuinely indefinite and is reported in info[b] (numpy LinAlgError at the API).
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, long long lda, long long strideA,
-                                                    int* __restrict__ info, int j0, const double* __restrict__ pol,
-                                                    int batch) {
-  extern __shared__ double sm[];
-  double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-  double(*Lo)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
-  __shared__ int bad, nclamp;
-  const int tid = threadIdx.x;
+// Row t of the block lives in the registers of thread t (64 threads, every loop fully unrolled so the row is
+// statically indexed); column j is scaled by its owner rows, published through shared memory and applied to
+// the trailing part of every row: two 64-thread barriers and 63 - j FMAs per column instead of shared-memory
+// read-modify-writes.  Entries right of the diagonal of a row are never read (they pick up garbage from the
+// unpredicated update and are stored as exact zeros).
+__global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                   int* __restrict__ info, int j0, const double* __restrict__ pol,
+                                                   int batch) {
+  __shared__ double col[NB];
+  __shared__ double ljj_sm;
+  const int t = threadIdx.x;
   const double floor_piv = pol[2 * blockIdx.x], neg_tol = pol[2 * blockIdx.x + 1];
   double* Ab = A + (long long)blockIdx.x * strideA + (long long)j0 * lda + j0;
-  if (tid == 0) bad = nclamp = 0;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    S[r][c] = (c <= r) ? Ab[(long long)r * lda + c] : 0.0;
-    Lo[r][c] = 0.0;
+  double s[NB];
+  {
+    const double2* row = reinterpret_cast<const double2*>(Ab + (long long)t * lda);
+#pragma unroll
+    for (int k = 0; k < NB; k += 2) {
+      const double2 v = row[k >> 1];
+      s[k] = (k <= t) ? v.x : 0.0;
+      s[k + 1] = (k + 1 <= t) ? v.y : 0.0;
+    }
   }
-  const int ur = tid >> 2, uc0 = tid & 3;  // trailing update: row ur, columns uc0 + 4q
+  int bad = 0, nclamp = 0;  // only meaningful in the thread that owns the pivot
+#pragma unroll
   for (int j = 0; j < NB; ++j) {
-    __syncthreads();  // trailing update of the previous column is complete
-    double piv = S[j][j];
-    if (!(piv >= floor_piv)) {  // also catches NaN
-      if (tid == 0) {
+    if (t == j) {
+      double piv = s[j];
+      if (!(piv >= floor_piv)) {  // also catches NaN
         if (piv > -neg_tol) ++nclamp;
-        else bad = (bad == 0) ? (j0 + j + 1) : bad;
+        else bad = j0 + j + 1;
+        piv = floor_piv;
       }
-      piv = floor_piv;
+      const double ljj = sqrt(piv);
+      s[j] = ljj;
+      ljj_sm = ljj;
     }
-    if (tid < NB && tid >= j) Lo[tid][j] = (tid == j) ? sqrt(piv) : S[tid][j] / sqrt(piv);
-    if (ur > j) {
-      const double lij = S[ur][j] / piv;  // l_ij * l_kj = s_ij * s_kj / piv
-#pragma unroll 4
-      for (int q = 0; q < 16; ++q) {
-        const int k = uc0 + 4 * q;
-        if (k > j && k <= ur) S[ur][k] = fma(-lij, S[k][j], S[ur][k]);
-      }
+    __syncthreads();
+    double l = 0.0;
+    if (t > j) {
+      l = s[j] / ljj_sm;
+      s[j] = l;
+      col[t] = l;
+    }
+    __syncthreads();
+    if (t > j) {
+#pragma unroll
+      for (int k = j + 1; k < NB; ++k) s[k] = fma(-l, col[k], s[k]);
     }
   }
-  __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    Ab[(long long)r * lda + c] = Lo[r][c];  // strict upper part of the block becomes exact zeros
+  {
+    double2* row = reinterpret_cast<double2*>(Ab + (long long)t * lda);
+#pragma unroll
+    for (int k = 0; k < NB; k += 2)
+      row[k >> 1] = make_double2((k <= t) ? s[k] : 0.0, (k + 1 <= t) ? s[k + 1] : 0.0);
   }
-  if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, bad);
-  if (tid == 0 && nclamp != 0) atomicAdd(&info[batch + blockIdx.x], nclamp);
+  // smallest failing pivot index wins (0 = none); earlier blocks were factored by earlier launches
+  if (bad != 0) {
+    int old = atomicCAS(&info[blockIdx.x], 0, bad);
+    while (old != 0 && old > bad) {
+      const int prev = atomicCAS(&info[blockIdx.x], old, bad);
+      if (prev == old) break;
+      old = prev;
+    }
+  }
+  if (nclamp != 0) atomicAdd(&info[batch + blockIdx.x], nclamp);
 }
 
 // ----------------------------------------------------------------------------------------- block inverses
@@ -170,39 +190,51 @@ __global__ void __launch_bounds__(256) chol_policy_kernel(double* __restrict__ p
 // explicit inverse of the diagonal block is NOT used here: it is not backward stable when the block is
 // ill conditioned (cfg1 reaches cond(K) ~ 1e15) and the trailing update then cancels catastrophically.
 // One CTA = 64 rows of the panel; thread r owns row r; L_jj is read from shared memory (broadcast).
-__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ A, long long lda, long long strideA,
-                                                         int j0, int rows) {
-  extern __shared__ double sm[];
-  double(*L)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-  double(*P)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+// One thread = one row of the panel, held in registers (64 doubles, loops fully unrolled); right-looking: as soon
+// as x_c is known the rest of the row is updated with column c of L_jj, read as 16-byte broadcasts from a
+// transposed copy in shared memory.  TRSM_ROWS rows per CTA.
+constexpr int TRSM_ROWS = 128;
+__global__ void __launch_bounds__(TRSM_ROWS) trsm_panel_kernel(double* __restrict__ A, long long lda,
+                                                               long long strideA, int j0, int rows) {
+  __shared__ __align__(16) double Lt[NB][NB + 2];  // Lt[c][k] = L_jj[k][c]; +2 keeps rows 16-byte aligned and spreads banks
   double* Ab = A + (long long)blockIdx.y * strideA;
   const double* Ljj = Ab + (long long)j0 * lda + j0;
-  const int r0 = blockIdx.x * NB;
-  double* Pg = Ab + (long long)(j0 + NB + r0) * lda + j0;
   const int tid = threadIdx.x;
-  const int live = min(NB, rows - r0);
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    L[r][c] = Ljj[(long long)r * lda + c];
-    P[r][c] = (r < live) ? Pg[(long long)r * lda + c] : 0.0;
+  for (int e = tid; e < NB * NB; e += TRSM_ROWS) {
+    const int k = e >> 6, c = e & 63;  // coalesced read of row k
+    Lt[c][k] = Ljj[(long long)k * lda + c];
   }
   __syncthreads();
+  const int r = blockIdx.x * TRSM_ROWS + tid;
+  if (r >= rows) return;
+  double* Pg = Ab + (long long)(j0 + NB + r) * lda + j0;
+  double p[NB];
   {
-    // 4 threads per row split the dot product over k mod 4; the 4 lanes of a row sit in one warp
-    const int r = tid >> 2, q = tid & 3;
-    for (int c = 0; c < NB; ++c) {
-      double s = 0.0;
-      for (int k = q; k < c; k += 4) s = fma(P[r][k], L[c][k], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) P[r][c] = (P[r][c] - s) / L[c][c];
-      __syncwarp();
+    const double2* row = reinterpret_cast<const double2*>(Pg);
+#pragma unroll
+    for (int k = 0; k < NB; k += 2) {
+      const double2 v = row[k >> 1];
+      p[k] = v.x;
+      p[k + 1] = v.y;
     }
   }
-  __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    if (r < live) Pg[(long long)r * lda + c] = P[r][c];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    const double x = p[c] / Lt[c][c];
+    p[c] = x;
+    // p[k] -= x * L[k][c] for k > c; pairs (k, k+1) with even k come from one 16-byte load
+    if ((c & 1) == 0) p[c + 1] = fma(-x, Lt[c][c + 1], p[c + 1]);
+#pragma unroll
+    for (int k = (c + 2) & ~1; k < NB; k += 2) {
+      const double2 lv = *reinterpret_cast<const double2*>(&Lt[c][k]);
+      p[k] = fma(-x, lv.x, p[k]);
+      p[k + 1] = fma(-x, lv.y, p[k + 1]);
+    }
+  }
+  {
+    double2* row = reinterpret_cast<double2*>(Pg);
+#pragma unroll
+    for (int k = 0; k < NB; k += 2) row[k >> 1] = make_double2(p[k], p[k + 1]);
   }
 }
 
@@ -310,28 +342,48 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
   static bool attr_set = false;
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
   if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     BO_CUDA(cudaFuncSetAttribute(block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    BO_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  for (int j0 = 0; j0 < npad; j0 += NB) {
-    potf2_kernel<<<batch, 256, smem, stream>>>(A, lda, strideA, info, j0, pol, batch);
-    BO_LAUNCH_CHECK("potf2_kernel");
-    const int r = npad - j0 - NB;
-    if (r <= 0) break;
-    double* P = A + (long long)(j0 + NB) * lda + j0;
-    trsm_panel_kernel<<<dim3((r + NB - 1) / NB, batch), 256, smem, stream>>>(A, lda, strideA, j0, r);
-    BO_LAUNCH_CHECK("trsm_panel_kernel");
-    int rc;
-    GemmArgs t;  // trailing -= P P^T (lower tiles only)
-    t.M = r; t.N = r; t.K = NB; t.alpha = -1.0; t.beta = 1.0;
-    t.A = P; t.lda = lda; t.strideA = strideA;
-    t.B = P; t.ldb = lda; t.strideB = strideA;
-    t.C = A + (long long)(j0 + NB) * (lda + 1); t.ldc = lda; t.strideC = strideA;
-    t.batch = batch; t.lower_only = 1;
-    rc = gemm(t, 0, 0, stream);
-    if (rc) return rc;
+  // Two-level blocking: inside an outer panel of NBO columns the 64-column steps update only the rest of that
+  // panel (rank-64 updates of a narrow strip); the trailing matrix is updated once per outer panel with K = NBO.
+  // A plain right-looking sweep with K = 64 reads and writes the whole trailing matrix 64 times per 4096 columns
+  // and is HBM-bound for large batches (cfg5: 512 matrices of 4096^2).
+  const int NBO = 4 * NB;
+  for (int J0 = 0; J0 < npad; J0 += NBO) {
+    const int Jend = (J0 + NBO < npad) ? J0 + NBO : npad;
+    for (int j0 = J0; j0 < Jend; j0 += NB) {
+      potf2_kernel<<<batch, NB, 0, stream>>>(A, lda, strideA, info, j0, pol, batch);
+      BO_LAUNCH_CHECK("potf2_kernel");
+      const int r = npad - j0 - NB;
+      if (r <= 0) break;
+      trsm_panel_kernel<<<dim3((r + TRSM_ROWS - 1) / TRSM_ROWS, batch), TRSM_ROWS, 0, stream>>>(A, lda, strideA, j0, r);
+      BO_LAUNCH_CHECK("trsm_panel_kernel");
+      const int nin = Jend - (j0 + NB);  // columns of the outer panel still to be factored
+      if (nin > 0) {
+        const double* P = A + (long long)(j0 + NB) * lda + j0;
+        GemmArgs t;  // strip [j0+NB, npad) x [j0+NB, Jend) -= P P^T (tiles above the diagonal skipped)
+        t.M = r; t.N = nin; t.K = NB; t.alpha = -1.0; t.beta = 1.0;
+        t.A = P; t.lda = lda; t.strideA = strideA;
+        t.B = P; t.ldb = lda; t.strideB = strideA;
+        t.C = A + (long long)(j0 + NB) * (lda + 1); t.ldc = lda; t.strideC = strideA;
+        t.batch = batch; t.lower_only = 1;
+        const int rc = gemm(t, 0, 0, stream);
+        if (rc) return rc;
+      }
+    }
+    const int ro = npad - Jend;
+    if (ro > 0) {
+      const double* P = A + (long long)Jend * lda + J0;
+      GemmArgs t;  // trailing [Jend, npad)^2 -= P P^T with the whole outer panel, K = Jend - J0
+      t.M = ro; t.N = ro; t.K = Jend - J0; t.alpha = -1.0; t.beta = 1.0;
+      t.A = P; t.lda = lda; t.strideA = strideA;
+      t.B = P; t.ldb = lda; t.strideB = strideA;
+      t.C = A + (long long)Jend * (lda + 1); t.ldc = lda; t.strideC = strideA;
+      t.batch = batch; t.lower_only = 1;
+      const int rc = gemm(t, 0, 0, stream);
+      if (rc) return rc;
+    }
   }
   block_inverse_kernel<<<dim3(npad / NB, batch), 256, smem, stream>>>(D, strideD, A, lda, strideA);
   BO_LAUNCH_CHECK("block_inverse_kernel");

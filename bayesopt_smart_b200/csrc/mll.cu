@@ -211,9 +211,20 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 static int group_settings(int npad, int m, int n_settings) {
-  // settings factored together: keep the matrices of one group near 4 GB
+  // settings factored together: the matrices of one group take up to 1/8 of the device memory (22 GB on a
+  // B200) -- the 64-column steps of the blocked Cholesky and the forward substitution are latency chains whose
+  // cost per group does not depend on how many matrices ride along
   const size_t per = (size_t)m * npad * npad * sizeof(double);
-  size_t g = ((size_t)4 << 30) / per;
+  static size_t budget = 0;
+  if (budget == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    budget = (size_t)4 << 30;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
+        prop.totalGlobalMem / 8 > budget)
+      budget = prop.totalGlobalMem / 8;
+  }
+  size_t g = budget / per;
   if (g < 1) g = 1;
   if (g > (size_t)n_settings) g = n_settings;
   return (int)g;
