@@ -287,7 +287,7 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
   FitBuffers fb;
   carve_fit(&fb, workspace_dev, npad, m);
   const long long strideA = (long long)npad * npad;
-  rc = gram(fb.A, npad, strideA, x_dev, ldx, 0, n, npad, d, m, hp, jitter, st);
+  rc = gram(fb.A, npad, strideA, x_dev, ldx, 0, n, npad, d, m, hp, jitter, st, /*lower_only=*/true);
   if (rc) return rc;
   rc = factor_and_invert(fb, npad, m, jitter, st);
   if (rc) return rc;

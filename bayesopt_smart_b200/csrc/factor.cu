@@ -21,20 +21,26 @@ namespace {
 constexpr int NB = 64;
 
 // ----------------------------------------------------------------------------------------- gram
+// LOWER = false (bo_gram_f64, the reference's update_k): tiles with bj >= bi, every value written to (i, j) and
+// mirrored to (j, i).  LOWER = true (the factorisations only read the lower triangle): tiles with bj <= bi, one
+// coalesced write per value; the mirror is kept only inside the 64-wide diagonal tiles so that every 64x64 tile the
+// blocked Cholesky touches is fully initialised.
+template <bool LOWER>
 __global__ void gram_kernel(double* __restrict__ K, long long ldk, long long strideK, const double* __restrict__ x,
                             int ldx, int last_eval, int n, int npad_rows, int d, int m, ObjParams hp,
                             double diag_add) {
-  // 16x16 pairs per block over the index range [last_eval, npad_rows); only tiles with bj >= bi
-  if (blockIdx.x < blockIdx.y) return;
-  const int i = last_eval + blockIdx.y * 16 + threadIdx.y;
+  // 16x16 pairs per block over the index range [last_eval, npad_rows)
+  if (LOWER ? (blockIdx.x > blockIdx.y) : (blockIdx.x < blockIdx.y)) return;
+  const int i = last_eval + blockIdx.y * 16 + threadIdx.y;  // row of the coalesced write
   const int j = last_eval + blockIdx.x * 16 + threadIdx.x;
-  if (i >= npad_rows || j >= npad_rows || j < i) return;
+  if (i >= npad_rows || j >= npad_rows || (LOWER ? j > i : j < i)) return;
+  const bool mirror = !LOWER || (blockIdx.x >> 2) == (blockIdx.y >> 2);
   if (i >= n || j >= n) {
     // identity padding keeps the padded factor trivially L = W = I
     const double v = (i == j) ? 1.0 : 0.0;
     for (int o = 0; o < m; ++o) {
       K[o * strideK + (long long)i * ldk + j] = v;
-      K[o * strideK + (long long)j * ldk + i] = v;
+      if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
     }
     return;
   }
@@ -47,7 +53,7 @@ __global__ void gram_kernel(double* __restrict__ K, long long ldk, long long str
     double v = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], kExp2Tab);
     if (i == j) v += diag_add;
     K[o * strideK + (long long)i * ldk + j] = v;
-    K[o * strideK + (long long)j * ldk + i] = v;
+    if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
   }
 }
 
@@ -324,12 +330,16 @@ __global__ void __launch_bounds__(256) pack_w_kernel(double* __restrict__ Wp, lo
 
 // =========================================================================================== host drivers
 int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, int last_eval, int n, int npad_rows,
-         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream) {
+         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream, bool lower_only) {
   const int span = npad_rows - last_eval;
   if (span <= 0) return BO_OK;
   const int nt = (span + 15) / 16;
-  gram_kernel<<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d, m, hp,
-                                                         diag_add);
+  if (lower_only)
+    gram_kernel<true><<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d,
+                                                                 m, hp, diag_add);
+  else
+    gram_kernel<false><<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d,
+                                                                  m, hp, diag_add);
   BO_LAUNCH_CHECK("gram_kernel");
   return BO_OK;
 }

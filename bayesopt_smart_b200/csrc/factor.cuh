@@ -6,7 +6,7 @@ namespace bo {
 
 // K (m, ldk, ldk): RBF Gram over rows/cols [last_eval, npad_rows); indices >= n get identity padding.
 int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, int last_eval, int n, int npad_rows,
-         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream);
+         int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream, bool lower_only = false);
 
 // In-place lower Cholesky of `batch` npad x npad matrices (npad % 64 == 0).  D receives the inverted 64x64
 // diagonal blocks (npad/64 blocks of 4096 doubles per matrix).  info holds 2*batch ints (zeroed by the caller):

@@ -307,7 +307,7 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
         hp.neg_half_inv_ls2[o] = -0.5 / (ls * ls);
       }
       int rc = gram(A + (long long)s * m * strideA, npad, strideA, x, ldx, 0, n, npad, d, m, hp, jitter[s0 + s],
-                    stream);
+                    stream, /*lower_only=*/true);
       if (rc) return rc;
     }
     BO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * g * m, stream));
