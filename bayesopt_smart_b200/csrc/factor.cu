@@ -97,14 +97,16 @@ __global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, long 
         else bad = j0 + j + 1;
         piv = floor_piv;
       }
-      const double ljj = sqrt(piv);
-      s[j] = ljj;
-      ljj_sm = ljj;
+      // one reciprocal square root per column on the critical path (instead of a square root followed by a
+      // division in every row): l_jj = piv * r, l_tj = s_tj * r, each within 1-2 ulp of the divided values
+      const double r = rsqrt(piv);
+      s[j] = piv * r;
+      ljj_sm = r;
     }
     __syncthreads();
     double l = 0.0;
     if (t > j) {
-      l = s[j] / ljj_sm;
+      l = s[j] * ljj_sm;
       s[j] = l;
       col[t] = l;
     }
