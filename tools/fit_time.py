@@ -28,7 +28,6 @@ for n, d in ((1024, 6), (2048, 8), (4096, 6)):
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    fit = orc.chol_fit(x, y, mu0, var0, ls, n) if n <= 2048 else None
     print(json.dumps(dict(kind="fit", n=n, d=d, fit_ms=float(np.median(ts)))), flush=True)
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -11,41 +11,11 @@ from bayesopt_smart_b200 import _lib  # noqa: E402
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
 from oracle import gp_oracle as orc  # noqa: E402
 
-S = 6
-
-
-def unpack_wpack(wp, npad):
-    """DMMA-packed W (common.cuh) -> dense lower-triangular (npad, npad)."""
-    nb = npad // 128
-    W = np.zeros((npad, npad))
-    r = np.arange(npad)[:, None]
-    k = np.arange(npad)[None, :]
-    ib, rr, kt, kk = r >> 7, r & 127, k >> 4, k & 15
-    wm, i, g = rr >> 6, (rr >> 3) & 7, rr & 7
-    sp, q, t = kk >> 3, (kk >> 2) & 1, kk & 3
-    off = (8 * ib * (ib + 1) // 2 + kt) * 2048 + (((wm * 8 + i) * 2 + sp) * 32 + (4 * g + t)) * 2 + q
-    mask = (k < (ib + 1) * 128) & (r >= 0)
-    W[np.broadcast_to(mask, W.shape)] = wp[np.broadcast_to(off, W.shape)[np.broadcast_to(mask, W.shape)]]
-    return np.tril(W)
-
-
-def balanced(q):
-    """int64 array -> S balanced digits, most significant first."""
-    out = [None] * S
-    r = q.copy()
-    for s in range(S - 1, 0, -1):
-        dgt = ((r + 128) & 255) - 128
-        out[s] = dgt
-        r = (r - dgt) >> 8
-    out[0] = r
-    return out
+from tests.i8_format import S, balanced_digits as balanced, planes_from_image, unpack_wpack  # noqa: E402
 
 
 def planes_from_buffer(buf, rows, nk):
-    """(nk, S, rows/8, 2, 8, 16) int8 image -> digits[s] of shape (rows, nk*32)."""
-    a = buf.view(np.int8).reshape(nk, S, rows // 8, 2, 8, 16)
-    a = a.transpose(1, 2, 4, 0, 3, 5).reshape(S, rows, nk * 32)
-    return a.astype(np.int64)
+    return planes_from_image(buf, rows, nk)
 
 
 def main():
