@@ -277,8 +277,27 @@ def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean
     n = int(current_eval)
     x_dev = to_device(x_vector[:n], _F64, dev)
     y_dev = to_device(y_vector[:n], _F64, dev)
-    cand_dev = to_device(input_space, None, dev)
+    ready = None
+    if isinstance(input_space, torch.Tensor) and input_space.device.type == "cpu" and input_space.is_pinned() \
+            and input_space.is_contiguous():
+        # the candidate upload (the largest transfer of the step) runs on a copy stream while the factorisation,
+        # which does not need the candidates, runs on the caller's stream
+        cand_dev = getattr(gp, "_cand_buf", None)
+        if cand_dev is None or cand_dev.shape != input_space.shape or cand_dev.dtype != input_space.dtype:
+            cand_dev = torch.empty(input_space.shape, dtype=input_space.dtype, device=dev)
+            gp._cand_buf = cand_dev
+        side = getattr(gp, "_copy_stream", None)
+        if side is None:
+            side = gp._copy_stream = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))  # earlier readers of the buffer have finished
+        with torch.cuda.stream(side):
+            cand_dev.copy_(input_space, non_blocking=True)
+            ready = side.record_event()
+    else:
+        cand_dev = to_device(input_space, None, dev)
     gp.fit(x_dev, y_dev, prior_mean, prior_variance, length_scales, n)
+    if ready is not None:
+        torch.cuda.current_stream(dev).wait_event(ready)
     n_cand = cand_dev.shape[0]
     cache = getattr(gp, "_iter_out", None)
     if cache is None or cache["acq"].numel() != n_cand or cache["mu"].shape[0] != gp.m:
