@@ -11,6 +11,8 @@
 //   alpha kernels      alpha = W^T (W (y - mu0))
 //   pack_w_kernel      W -> 16 KB tiles in DMMA fragment order for trmm.cu
 #include "factor.cuh"
+
+#include <stdlib.h>
 #include "gemm.cuh"
 #include "rbf.cuh"
 
@@ -21,39 +23,69 @@ namespace {
 constexpr int NB = 64;
 
 // ----------------------------------------------------------------------------------------- gram
-// LOWER = false (bo_gram_f64, the reference's update_k): tiles with bj >= bi, every value written to (i, j) and
-// mirrored to (j, i).  LOWER = true (the factorisations only read the lower triangle): tiles with bj <= bi, one
-// coalesced write per value; the mirror is kept only inside the 64-wide diagonal tiles so that every 64x64 tile the
-// blocked Cholesky touches is fully initialised.
+// 64x64 tile of pairs per CTA (256 threads, 16 pairs each); the tile's two sets of training rows and the exp table
+// are staged in shared memory, every value is written with coalesced 128-byte row segments.
+// LOWER = false (bo_gram_f64, the reference's update_k): tiles with bj >= bi; the mirror (j, i) is written too.
+// LOWER = true (the factorisations only read the lower triangle): tiles with bj <= bi, one write per value; the
+// mirror is kept only in the diagonal tiles so that every 64x64 tile the blocked Cholesky touches is initialised.
+// The grid is the triangular list of tiles (no empty CTAs).
+constexpr int GT = 64;
 template <bool LOWER>
-__global__ void gram_kernel(double* __restrict__ K, long long ldk, long long strideK, const double* __restrict__ x,
-                            int ldx, int last_eval, int n, int npad_rows, int d, int m, ObjParams hp,
-                            double diag_add) {
-  // 16x16 pairs per block over the index range [last_eval, npad_rows)
-  if (LOWER ? (blockIdx.x > blockIdx.y) : (blockIdx.x < blockIdx.y)) return;
-  const int i = last_eval + blockIdx.y * 16 + threadIdx.y;  // row of the coalesced write
-  const int j = last_eval + blockIdx.x * 16 + threadIdx.x;
-  if (i >= npad_rows || j >= npad_rows || (LOWER ? j > i : j < i)) return;
-  const bool mirror = !LOWER || (blockIdx.x >> 2) == (blockIdx.y >> 2);
-  if (i >= n || j >= n) {
-    // identity padding keeps the padded factor trivially L = W = I
-    const double v = (i == j) ? 1.0 : 0.0;
-    for (int o = 0; o < m; ++o) {
-      K[o * strideK + (long long)i * ldk + j] = v;
-      if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
+__global__ void __launch_bounds__(256)
+    gram_kernel(double* __restrict__ K, long long ldk, long long strideK, const double* __restrict__ x, int ldx,
+                int last_eval, int n, int npad_rows, int d, int m, ObjParams hp, double diag_add) {
+  __shared__ double exp_tab[64];
+  __shared__ double xi[GT][BO_MAX_DIMS + 1];   // rows of the tile (read as broadcasts)
+  __shared__ double xjT[BO_MAX_DIMS][GT];      // columns of the tile, transposed (lanes read consecutive words)
+  const int tid = threadIdx.x;
+  if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
+  // triangular tile index -> (big, small) with small <= big
+  int big = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((long long)big * (big + 1) / 2 > (long long)blockIdx.x) --big;
+  while ((long long)(big + 1) * (big + 2) / 2 <= (long long)blockIdx.x) ++big;
+  const int small = blockIdx.x - big * (big + 1) / 2;
+  const int bi = LOWER ? big : small, bj = LOWER ? small : big;  // tile row / column
+  const int i0 = last_eval + bi * GT, j0 = last_eval + bj * GT;
+  for (int e = tid; e < GT * d; e += 256) {
+    const int r = e / d, k = e - r * d;
+    const int gi = i0 + r, gj = j0 + r;
+    xi[r][k] = gi < n ? x[(long long)gi * ldx + k] : 0.0;
+    xjT[k][r] = gj < n ? x[(long long)gj * ldx + k] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool mirror = !LOWER || bi == bj;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int r = ty * 4 + a;
+    const int i = i0 + r;
+    if (i >= npad_rows) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cc = tx + 16 * c;
+      const int j = j0 + cc;
+      if (j >= npad_rows || (bi == bj && (LOWER ? j > i : j < i))) continue;
+      if (i >= n || j >= n) {
+        // identity padding keeps the padded factor trivially L = W = I
+        const double v = (i == j) ? 1.0 : 0.0;
+        for (int o = 0; o < m; ++o) {
+          K[o * strideK + (long long)i * ldk + j] = v;
+          if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
+        }
+        continue;
+      }
+      double sq = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double diff = xi[r][k] - xjT[k][cc];
+        sq = fma(diff, diff, sq);
+      }
+      for (int o = 0; o < m; ++o) {
+        double v = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], exp_tab);
+        if (i == j) v += diag_add;
+        K[o * strideK + (long long)i * ldk + j] = v;
+        if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
+      }
     }
-    return;
-  }
-  double sq = 0.0;
-  for (int k = 0; k < d; ++k) {
-    const double diff = x[(long long)i * ldx + k] - x[(long long)j * ldx + k];
-    sq = fma(diff, diff, sq);
-  }
-  for (int o = 0; o < m; ++o) {
-    double v = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], kExp2Tab);
-    if (i == j) v += diag_add;
-    K[o * strideK + (long long)i * ldk + j] = v;
-    if (mirror) K[o * strideK + (long long)j * ldk + i] = v;
   }
 }
 
@@ -335,13 +367,12 @@ int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, 
          int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream, bool lower_only) {
   const int span = npad_rows - last_eval;
   if (span <= 0) return BO_OK;
-  const int nt = (span + 15) / 16;
+  const int nt = (span + GT - 1) / GT;
+  const unsigned tiles = (unsigned)((long long)nt * (nt + 1) / 2);
   if (lower_only)
-    gram_kernel<true><<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d,
-                                                                 m, hp, diag_add);
+    gram_kernel<true><<<tiles, 256, 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d, m, hp, diag_add);
   else
-    gram_kernel<false><<<dim3(nt, nt), dim3(16, 16), 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d,
-                                                                  m, hp, diag_add);
+    gram_kernel<false><<<tiles, 256, 0, stream>>>(K, ldk, strideK, x, ldx, last_eval, n, npad_rows, d, m, hp, diag_add);
   BO_LAUNCH_CHECK("gram_kernel");
   return BO_OK;
 }
@@ -361,7 +392,7 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
   // panel (rank-64 updates of a narrow strip); the trailing matrix is updated once per outer panel with K = NBO.
   // A plain right-looking sweep with K = 64 reads and writes the whole trailing matrix 64 times per 4096 columns
   // and is HBM-bound for large batches (cfg5: 512 matrices of 4096^2).
-  const int NBO = 4 * NB;
+  const int NBO = 4 * NB;  // 128 / 512 / 1024 measured within 6 % of each other on the cfg5 sweep; 256 is the best
   for (int J0 = 0; J0 < npad; J0 += NBO) {
     const int Jend = (J0 + NBO < npad) ? J0 + NBO : npad;
     for (int j0 = J0; j0 < Jend; j0 += NB) {
