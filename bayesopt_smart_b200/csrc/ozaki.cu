@@ -553,24 +553,33 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       const double f24 = f * (1.0 / 16777216.0);
       mbar_wait(tmem_full, acc_phase);
       tc_fence_after();
+      // software pipeline over chunks of 4 columns: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+      // recombined, and the accumulators are handed back to the MMA warps as soon as the last load has landed
+      // (before the arithmetic of the last chunk)
+      int a[2][OZ_PLANES][4];
+#pragma unroll
+      for (int gq = 0; gq < OZ_PLANES; ++gq) tmem_ld4(acc_addr + gq * OZ_TN, a[0][gq]);
 #pragma unroll
       for (int c0 = 0; c0 < OZ_EC; c0 += 4) {
-        int a[OZ_PLANES][4];
+        const int cur = (c0 >> 2) & 1;
+        tmem_ld_wait(a[cur]);
+        if (c0 + 4 < OZ_EC) {
 #pragma unroll
-        for (int gq = 0; gq < OZ_PLANES; ++gq) tmem_ld4(acc_addr + gq * OZ_TN + c0, a[gq]);
-        tmem_ld_wait(a);
+          for (int gq = 0; gq < OZ_PLANES; ++gq) tmem_ld4(acc_addr + gq * OZ_TN + c0 + 4, a[cur ^ 1][gq]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           // V = f (b0 + 2^-24 b1),  b0 = (a0 256 + a1) 256 + a2,  b1 = (a3 256 + a4) 256 + a5   (exact int64)
-          const double b0 = triple_to_double(a[0][j], a[1][j], a[2][j]);
-          const double b1 = triple_to_double(a[3][j], a[4][j], a[5][j]);
+          const double b0 = triple_to_double(a[cur][0][j], a[cur][1][j], a[cur][2][j]);
+          const double b1 = triple_to_double(a[cur][3][j], a[cur][4][j], a[cur][5][j]);
           const double v = fma(b1, f24, b0 * f);
           ssum[c0 + j] = fma(v, v, ssum[c0 + j]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
       acc_phase ^= 1;
       const bool unit_done = oz_cursor_next_block(dc, unit_stride, total_units, nsplit, nb);
       if (unit_done) {
