@@ -236,3 +236,16 @@ def test_parity_edge_and_full_size_suites_pass_with_the_int8_engine_as_default(e
     r = subprocess.run([sys.executable, "-m", "pytest", *files, "-m", "gpu", "-q", "-x"], cwd=root, env=env2,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_randomised_shapes_are_deterministic_and_within_tau(env):
+    """tools/oz_stress.py: random (n, d, m, candidates, length scale) cases; every case is scored twice with the INT8
+    engine (bit-identical) and compared with the FP64 engine (tolerance max(1e-9, 10 eps cond))."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join("tools", "oz_stress.py"), "40", "7"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
