@@ -17,17 +17,21 @@
 // so one cp.async.bulk per operand per k-step fills a pipeline stage, and the smem descriptor is
 // (start, LBO = 128 B between the two k halves, SBO = 256 B between row groups).
 //
-// Kernel.  One CTA per SM, persistent.  Warp 0: bulk-copy producer; warps 1 and 10: TMEM allocator + the two
-// alternating MMA issuers; warps 2-9: A-operand feeders and epilogue, two warps per TMEM lane quarter with 32 columns each (tcgen05.ld, integer recombination in
-// triples, two exact int64 -> FP64 conversions, row scale, square, running per-thread sums over all row blocks
-// of the work unit; one transposed shuffle reduction per unit).
+// Kernel (oz_sumsq_kernel).  One CTA of 11 warps per SM, persistent; a work unit is (candidate tile of 64,
+// objective, row split) and the CTA walks all row blocks of the unit.
+//   warp 0        bulk-copy producer, 5 stages of 36 KB (one k-step of W planes + K* planes)
+//   warps 1, 10   the two MMA issuers, alternating k-steps: 21 tcgen05.mma.kind::i8 128x64x32 per k-step into
+//                 6 TMEM accumulators (384 columns); warp 1 also allocates / frees TMEM
+//   warps 2-9     during the k loop: A-operand feeders; at the end of a row block: epilogue, two warps per TMEM
+//                 lane quarter with 32 columns each (tcgen05.ld, integer recombination in triples, two exact
+//                 int64 -> FP64 conversions, row scale, square, running per-thread sums over all row blocks of
+//                 the unit; one transposed shuffle reduction per unit)
 // The W planes are the MMA's A operand and are read from TENSOR MEMORY: with A in shared memory a 128 x N x 32
 // kind::i8 MMA takes N/2 + 43 cycles on B200 (the 4 KB A read is not hidden: tools/umma_probe.cu), from TMEM it
-// takes N/2.  Per k-step the eight epilogue warps (idle during the k loop) move the six 4 KB A planes shared
-// memory -> registers -> TMEM (ld.shared.v4 + tcgen05.st.32x32b.x8, two alternating 48-column slots) and the
-// issuing thread runs the 21 MMAs 128x64x32 into the 6 accumulators (384 columns).  tcgen05.cp from the
-// issuing thread was measured and rejected: it shares the in-order pipe with the MMAs (939 vs 672 cycles per
-// k-step, tools/umma_probe2.cu; the register path: 845 with the handshake, tools/umma_probe3.cu).
+// takes N/2.  Per k-step the feeder warps move the six 4 KB A planes shared memory -> registers -> TMEM
+// (ld.shared.v4 + tcgen05.st.32x32b.x8, two alternating 48-column slots).  tcgen05.cp from the issuing thread
+// was measured and rejected: it shares the in-order pipe with the MMAs (939 vs 672 cycles per k-step,
+// tools/umma_probe2.cu; the register path: 845 with the handshake, tools/umma_probe3.cu).
 #include "ozaki.cuh"
 
 #include <stdlib.h>
@@ -39,7 +43,7 @@ namespace bo {
 namespace {
 
 constexpr int OZ_STAGES = 5;
-constexpr int OZ_THREADS = 352;  // producer warp, MMA warp, 8 feeder / epilogue warps, second MMA warp
+constexpr int OZ_THREADS = 352;     // producer warp, MMA warp, 8 feeder / epilogue warps, second MMA warp
 constexpr int OZ_EC = OZ_TN / 2;     // accumulator columns per epilogue warp
 constexpr int OZ_STAGE_BYTES = OZ_A_STAGE + OZ_B_STAGE;  // 36864
 constexpr int OZ_ASLOT_COL = OZ_PLANES * OZ_TN;          // first TMEM column of the two A-operand slots
@@ -803,7 +807,6 @@ OzPlan make_oz_plan(int n, int m, long long n_cand) {
   if (ct < 1) ct = 1;
   p.chunk_tiles = (int)ct;
   p.ld_chunk = ct * OZ_TN;
-  p.nbuf = 1;
   p.kq_bytes = (size_t)m * ct * tile_bytes;
   p.part_doubles = (size_t)m * p.nsplit * p.ld_chunk;
   p.mean_doubles = (size_t)m * p.ld_chunk;
@@ -811,7 +814,7 @@ OzPlan make_oz_plan(int n, int m, long long n_cand) {
 }
 
 size_t oz_workspace_bytes(const OzPlan& p) {
-  return p.nbuf * (align256(p.kq_bytes) + align256(p.mean_doubles * 8)) + align256(p.part_doubles * 8);
+  return align256(p.kq_bytes) + align256(p.mean_doubles * 8) + align256(p.part_doubles * 8);
 }
 
 int oz_score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, int ldc, long long n_cand,

@@ -26,7 +26,6 @@ struct OzPlan {
   int nsplit = 1;           // row blocks of one candidate tile are dealt to nsplit CTAs (keeps K* tiles in L2)
   int chunk_tiles = 0;      // candidate tiles (of 64) per chunk
   long long ld_chunk = 0;   // chunk_tiles * 64
-  int nbuf = 1;
   size_t kq_bytes = 0, part_doubles = 0, mean_doubles = 0;
 };
 OzPlan make_oz_plan(int n, int m, long long n_cand);
