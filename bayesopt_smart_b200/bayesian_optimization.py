@@ -16,7 +16,7 @@ import torch
 from . import config as cfg
 from . import distributed as bd
 from .acquisition import exact_hvi_device
-from .engine import DeviceGP, PinnedMirror, require_cuda, to_device
+from .engine import DeviceGP, PinnedMirror, grid_candidates, require_cuda, to_device
 from .numba_kernels import (compute_prior_mean, compute_prior_variance, initialize_lhs_integer,
                             optimize_hyperparams_mll)
 from .pareto import compute_pareto_front, is_pareto_efficient, print_pareto_analysis
@@ -67,7 +67,8 @@ def _gather_shards(out, per_rank, n_total):
 def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, variance_objectives, std_mu_objectives,
              std_variance_objectives, ucb, acquisition_values, input_space, prior_mean, prior_variance,
              reference_point, n_evaluations, total_samples, n_objectives, function, betas, length_scales,
-             batch_size, bounds, callbacks=None, acquisition="sum_ucb", variance_engine=None):
+             batch_size, bounds, callbacks=None, acquisition="sum_ucb", variance_engine=None,
+             candidates_from_bounds=False):
     """The BO loop; same parameters and return value as the reference (:51-247).
 
     Each iteration: Powell fit of (length_scales, prior_variance) on the GPU log marginal likelihood,
@@ -89,7 +90,10 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
     gp = DeviceGP(device, variance_engine=variance_engine)
     rank, world = bd.world_info()
     lo, hi = bd.shard_range(input_space.shape[0], world, rank)
-    candidates = to_device(input_space[lo:hi], None, device)  # this rank's shard, uploaded once, stays in HBM
+    if candidates_from_bounds:  # input_space is the integer grid of `bounds`: this rank's rows are generated in HBM
+        candidates = grid_candidates(bounds, lo, hi - lo, device)
+    else:
+        candidates = to_device(input_space[lo:hi], None, device)  # this rank's shard, uploaded once, stays in HBM
     n_cand, m = candidates.shape[0], y_vector.shape[1]
     per_rank = bd.shard_range(input_space.shape[0], world, 0)[1]
     out = {k: torch.empty((n_cand,) if k == "acq" else (m, n_cand), dtype=torch.float64, device=device)
@@ -180,6 +184,7 @@ class BayesianOptimization:
         # candidate set: every integer point of the box, upper bounds exclusive (:338-340)
         axes = np.meshgrid(*[np.arange(lo, hi) for lo, hi in bounds], indexing="ij")
         self.input_space = np.stack([a.ravel() for a in axes], axis=-1)
+        self._grid_input_space = self.input_space  # optimize() regenerates it on the device unless it was replaced
         n_cand = len(self.input_space)
 
         self.total_samples = self.initial_samples + self.n_iterations * self.batch_size
@@ -209,7 +214,8 @@ class BayesianOptimization:
                     "n_objectives", "function", "betas", "length_scales", "batch_size", "bounds")}
         self.x_vector, self.y_vector, self.n_evaluations = optimize(
             **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition,
-            variance_engine=self.variance_engine)
+            variance_engine=self.variance_engine,
+            candidates_from_bounds=self.input_space is self._grid_input_space)
 
     def pareto_analysis(self) -> np.ndarray:
         """Pareto-efficient objective rows among the evaluated points (reference :465-488)."""

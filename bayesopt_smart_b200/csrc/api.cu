@@ -117,6 +117,22 @@ __global__ void pad_copy_kernel(double* __restrict__ A, int npad, const double* 
   A[((long long)o * npad + i) * npad + j] = v;
 }
 
+struct GridSpec {
+  long long lo[BO_MAX_DIMS], extent[BO_MAX_DIMS];
+};
+// row i of the C-ordered grid: mixed-radix digits of i, last dimension fastest
+__global__ void grid_kernel(long long* __restrict__ out, long long ld, GridSpec g, int d, long long row0,
+                            long long rows) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  long long i = row0 + r;
+  for (int k = d - 1; k >= 0; --k) {
+    const long long q = i / g.extent[k];
+    out[r * ld + k] = g.lo[k] + (i - q * g.extent[k]);
+    i = q;
+  }
+}
+
 struct FitBuffers {
   double *A, *W, *T, *D, *scratch, *pol;
   int* info;
@@ -463,6 +479,25 @@ int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n
   BO_REQUIRE(hvi_dev && ucb_dev && ref_host && (front_dev || n_front == 0), "null pointer");
   BO_REQUIRE(m == 2 || m == 3, "exact HVI supports 2 or 3 objectives");
   return hvi(hvi_dev, ucb_dev, ld, n_cand, m, front_dev, n_front, ref_host, (cudaStream_t)stream);
+}
+
+int bo_grid_i64(long long* out_dev, long long ld, const long long* lo_host, const long long* hi_host, int d,
+                long long row0, long long rows, void* stream) {
+  BO_REQUIRE(out_dev && lo_host && hi_host, "null pointer");
+  BO_REQUIRE(d >= 1 && d <= BO_MAX_DIMS && ld >= d && row0 >= 0 && rows >= 0, "bad sizes");
+  GridSpec g;
+  long long total = 1;
+  for (int k = 0; k < d; ++k) {
+    BO_REQUIRE(hi_host[k] > lo_host[k], "empty grid dimension");
+    g.lo[k] = lo_host[k];
+    g.extent[k] = hi_host[k] - lo_host[k];
+    total *= g.extent[k];
+  }
+  BO_REQUIRE(row0 + rows <= total, "row range exceeds the grid");
+  if (rows == 0) return BO_OK;
+  grid_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, ld, g, d, row0, rows);
+  BO_LAUNCH_CHECK("grid_kernel");
+  return BO_OK;
 }
 
 int bo_kstar_dense_f64(double* kstar_dev, long long ld_row, long long ld_obj, const double* x_dev, int ldx,

@@ -66,6 +66,25 @@ def to_device(a, dtype=None, device=None) -> torch.Tensor:
     return torch.from_numpy(arr).to(device)
 
 
+def grid_candidates(bounds, row0: int = 0, rows: Optional[int] = None, device=None) -> torch.Tensor:
+    """Rows [row0, row0 + rows) of the reference's candidate set -- every integer point of the box ``bounds``
+    (upper bounds exclusive), C order (bayesian_optimization.py:338-340) -- generated on the device."""
+    device = device or require_cuda()
+    lo = np.ascontiguousarray([int(b[0]) for b in bounds], dtype=np.int64)
+    hi = np.ascontiguousarray([int(b[1]) for b in bounds], dtype=np.int64)
+    total = int(np.prod(hi - lo))
+    rows = total - row0 if rows is None else int(rows)
+    if np.any(hi <= lo) or row0 < 0 or rows < 0 or row0 + rows > total:
+        raise _lib.BoError(f"grid_candidates: bad bounds / row range ({bounds}, row0={row0}, rows={rows})")
+    out = torch.empty((rows, len(lo)), dtype=torch.int64, device=device)
+    if rows == 0:
+        return out
+    ll = ctypes.POINTER(ctypes.c_longlong)
+    _lib.check(_lib.load().bo_grid_i64(_ptr(out), out.stride(0), lo.ctypes.data_as(ll),
+                                       hi.ctypes.data_as(ll), len(lo), int(row0), rows, _stream()))
+    return out
+
+
 def candidate_kind(cand: torch.Tensor) -> int:
     if cand.dtype == torch.float64:
         return _lib.BO_CAND_F64

@@ -203,6 +203,14 @@ int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const doub
 int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n_cand, int m,
                const double* front_dev, int n_front, const double* ref_host, void* stream);
 
+/* ------------------------------------------------------ candidate set on the device
+ * Rows [row0, row0 + rows) of the integer Cartesian grid prod_k [lo_k, hi_k) in C order -- what the reference
+ * builds on the host with np.meshgrid(*[np.arange(lo, hi)], indexing="ij") raveled
+ * (bayesian_optimization.py:338-340).  out is (rows, ld) int64, d <= BO_MAX_DIMS.  A rank of a sharded run
+ * generates its own slice instead of receiving it over PCIe.                                          */
+int bo_grid_i64(long long* out_dev, long long ld, const long long* lo_host, const long long* hi_host, int d,
+                long long row0, long long rows, void* stream);
+
 /* ---------------------------------------------- function-level drop-ins on dense arrays
  * The reference's free functions exchange a materialised k_star (m, T, M).  These keep
  * that contract for callers that use the functions one by one.

@@ -171,3 +171,40 @@ def test_error_paths(pkg):
     gp.fit(xd, yd, mu0, var0, ls, 20)
     out = gp.score(cand, betas)
     assert torch.isfinite(out["mu"]).all() and torch.isfinite(out["var"]).all()
+
+
+def test_device_grid_generator_matches_meshgrid(pkg):
+    """bo_grid_i64 / engine.grid_candidates: the reference's candidate set (bayesian_optimization.py:338-340),
+    whole and in shards, bit for bit."""
+    from bayesopt_smart_b200.engine import grid_candidates
+
+    for bounds in ([(0, 300), (0, 300)], [(-3, 4), (10, 13), (0, 5)], [(0, 10)] * 6, [(5, 6), (0, 7)], [(2, 9)]):
+        axes = np.meshgrid(*[np.arange(lo, hi) for lo, hi in bounds], indexing="ij")
+        want = np.stack([a.ravel() for a in axes], axis=-1)
+        got = grid_candidates(bounds)
+        assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+        total = want.shape[0]
+        for lo, hi in ((0, 1), (total // 3, total // 3 + min(1000, total - total // 3)), (total - 1, total), (5, 5)):
+            if lo <= hi <= total:
+                assert np.array_equal(grid_candidates(bounds, lo, hi - lo).cpu().numpy(), want[lo:hi])
+    from bayesopt_smart_b200._lib import BoError
+
+    with pytest.raises(BoError):
+        grid_candidates([(0, 4), (3, 3)])
+
+
+def test_optimize_with_replaced_input_space_uses_it(pkg):
+    """A caller that swaps `input_space` for its own candidate list gets that list scored (not the regenerated grid)."""
+    def toy(xv):
+        return np.array([-(xv[0] - 7.0) ** 2, -(xv[1] - 3.0) ** 2])
+
+    bo = pkg.BayesianOptimization(toy, [(0, 12), (0, 12)], n_objectives=2, n_iterations=2, initial_samples=6,
+                                  batch_size=2)
+    keep = bo.input_space[(bo.input_space[:, 0] % 2 == 0)]
+    bo.input_space = keep
+    for name in ("mu_objectives", "variance_objectives", "std_mu_objectives", "std_variance_objectives", "ucb"):
+        setattr(bo, name, np.zeros((2, len(keep))))
+    bo.acquisition_values = np.zeros(len(keep))
+    bo.optimize()
+    new_rows = bo.x_vector[6:10]
+    assert np.all(new_rows[:, 0] % 2 == 0)
