@@ -3,7 +3,7 @@
 // identity block in the padding, so every GEMM below runs on whole tiles.
 //
 //   gram_kernel        K = var * exp(-0.5 |xi-xj|^2 / ls^2) (+ diag_add), identity padding
-//   potf2_kernel       64x64 diagonal block: one row per thread in registers, column broadcast through smem
+//   potf2_kernel       64x64 diagonal block: rows in registers (4 threads per row), column broadcast through smem
 //   trsm_panel_kernel  panel <- panel * L_jj^-T by substitution (backward stable, like dtrsm), row per thread
 //   block_inverse      inverses of all diagonal blocks in parallel (base of W = L^-1 and of the MLL solve)
 //   cholesky_blocked   right-looking: potf2 -> panel TRSM -> trailing SYRK (DMMA)
@@ -90,40 +90,37 @@ __global__ void __launch_bounds__(256)
 }
 
 // ----------------------------------------------------------------------------------------- potf2
-// One CTA (64 threads) per matrix in the batch: lower Cholesky factor of the 64x64 diagonal block.
+// One CTA (256 threads) per matrix in the batch: lower Cholesky factor of the 64x64 diagonal block.
 //
 // Pivot policy (pol[2b] = floor, pol[2b+1] = negative tolerance): in exact arithmetic every pivot of
 // K + jitter*I is >= jitter, so a pivot that rounding pushed below the floor -- but not below -tolerance --
 // is clamped to the floor (counted in info[batch + b]); a pivot below -tolerance or NaN means the input is
 // genuinely indefinite and is reported in info[b] (numpy LinAlgError at the API).
-// Row t of the block lives in the registers of thread t (64 threads, every loop fully unrolled so the row is
-// statically indexed); column j is scaled by its owner rows, published through shared memory and applied to
-// the trailing part of every row: two 64-thread barriers and 63 - j FMAs per column instead of shared-memory
-// read-modify-writes.  Entries right of the diagonal of a row are never read (they pick up garbage from the
-// unpredicated update and are stored as exact zeros).
-__global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, long long lda, long long strideA,
-                                                   int* __restrict__ info, int j0, const double* __restrict__ pol,
-                                                   int batch) {
+// Four threads per row: thread (t, q) keeps the columns k = q, q+4, ... of row t in registers (16 values, every
+// loop fully unrolled so they are statically indexed).  Per column j: the owner of the pivot publishes
+// r = 1/sqrt(pivot), the owners of column j scale their entry and publish it, then every thread updates its
+// trailing entries with 16 - j/4 FMAs: two block barriers per column and a quarter of the serial FMA chain of a
+// row-per-thread layout.
+__global__ void __launch_bounds__(4 * NB) potf2_kernel(double* __restrict__ A, long long lda, long long strideA,
+                                                       int* __restrict__ info, int j0, const double* __restrict__ pol,
+                                                       int batch) {
   __shared__ double col[NB];
-  __shared__ double ljj_sm;
-  const int t = threadIdx.x;
+  __shared__ double rinv_sm;
+  const int t = threadIdx.x >> 2, q = threadIdx.x & 3;
   const double floor_piv = pol[2 * blockIdx.x], neg_tol = pol[2 * blockIdx.x + 1];
-  double* Ab = A + (long long)blockIdx.x * strideA + (long long)j0 * lda + j0;
-  double s[NB];
-  {
-    const double2* row = reinterpret_cast<const double2*>(Ab + (long long)t * lda);
+  double* row = A + (long long)blockIdx.x * strideA + (long long)(j0 + t) * lda + j0;
+  double s[NB / 4];
 #pragma unroll
-    for (int k = 0; k < NB; k += 2) {
-      const double2 v = row[k >> 1];
-      s[k] = (k <= t) ? v.x : 0.0;
-      s[k + 1] = (k + 1 <= t) ? v.y : 0.0;
-    }
+  for (int i = 0; i < NB / 4; ++i) {
+    const int k = q + 4 * i;
+    s[i] = (k <= t) ? row[k] : 0.0;
   }
   int bad = 0, nclamp = 0;  // only meaningful in the thread that owns the pivot
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (t == j) {
-      double piv = s[j];
+    const int ij = j >> 2, qj = j & 3;  // register index / owner lane of column j
+    if (t == j && q == qj) {
+      double piv = s[ij];
       if (!(piv >= floor_piv)) {  // also catches NaN
         if (piv > -neg_tol) ++nclamp;
         else bad = j0 + j + 1;
@@ -132,27 +129,27 @@ __global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, long 
       // one reciprocal square root per column on the critical path (instead of a square root followed by a
       // division in every row): l_jj = piv * r, l_tj = s_tj * r, each within 1-2 ulp of the divided values
       const double r = rsqrt(piv);
-      s[j] = piv * r;
-      ljj_sm = r;
+      s[ij] = piv * r;
+      rinv_sm = r;
     }
     __syncthreads();
-    double l = 0.0;
-    if (t > j) {
-      l = s[j] * ljj_sm;
-      s[j] = l;
+    if (t > j && q == qj) {
+      const double l = s[ij] * rinv_sm;
+      s[ij] = l;
       col[t] = l;
     }
     __syncthreads();
     if (t > j) {
+      const double l = col[t];
+      if (q > qj) s[ij] = fma(-l, col[q + 4 * ij], s[ij]);  // the entries of this register right of column j
 #pragma unroll
-      for (int k = j + 1; k < NB; ++k) s[k] = fma(-l, col[k], s[k]);
+      for (int i = ij + 1; i < NB / 4; ++i) s[i] = fma(-l, col[q + 4 * i], s[i]);
     }
   }
-  {
-    double2* row = reinterpret_cast<double2*>(Ab + (long long)t * lda);
 #pragma unroll
-    for (int k = 0; k < NB; k += 2)
-      row[k >> 1] = make_double2((k <= t) ? s[k] : 0.0, (k + 1 <= t) ? s[k + 1] : 0.0);
+  for (int i = 0; i < NB / 4; ++i) {
+    const int k = q + 4 * i;
+    row[k] = (k <= t) ? s[i] : 0.0;  // strict upper part of the block becomes exact zeros
   }
   // smallest failing pivot index wins (0 = none); earlier blocks were factored by earlier launches
   if (bad != 0) {
@@ -396,7 +393,7 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
   for (int J0 = 0; J0 < npad; J0 += NBO) {
     const int Jend = (J0 + NBO < npad) ? J0 + NBO : npad;
     for (int j0 = J0; j0 < Jend; j0 += NB) {
-      potf2_kernel<<<batch, NB, 0, stream>>>(A, lda, strideA, info, j0, pol, batch);
+      potf2_kernel<<<batch, 4 * NB, 0, stream>>>(A, lda, strideA, info, j0, pol, batch);
       BO_LAUNCH_CHECK("potf2_kernel");
       const int r = npad - j0 - NB;
       if (r <= 0) break;
