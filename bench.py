@@ -302,7 +302,7 @@ def run_gpu_arm(args):
         import ctypes as _ct
 
         pk = _ct.c_double()
-        _lib.check(lib.bo_i8_peak_tops(_ct.byref(pk), 0.03, None))
+        _lib.check(lib.bo_i8_peak_tops(_ct.byref(pk), 0.4, None))  # sustained (see int8_engine.roofline)
         peak_i8_tops = pk.value
 
     for _ in range(max(args.warmup, 3)):
@@ -358,10 +358,14 @@ def run_gpu_arm(args):
         for _ in range(2):
             step_e2e(gp8)
         secs8_e2e, _ = timed_steps(lambda: step_e2e(gp8), args.steps)
-        peak8 = ctypes.c_double()
-        _lib.check(lib.bo_i8_peak_tops(ctypes.byref(peak8), 0.03, None))
+        # the roofline denominator: the kernel's own MMA batch on resident operands, as a 30 ms burst and sustained
+        # for 0.4 s (the contraction is timed inside long steps, so the sustained figure is the one it is held to)
+        peak8b, peak8 = ctypes.c_double(), ctypes.c_double()
+        _lib.check(lib.bo_i8_peak_tops(ctypes.byref(peak8b), 0.03, None))
+        _lib.check(lib.bo_i8_peak_tops(ctypes.byref(peak8), 0.4, None))
         i8 = dict(secs=secs8, secs_e2e=secs8_e2e, ms=ms8.value, launches=int(nl8.value), flops=fl8.value,
-                  gpu_launches=launches8, dacq=dacq, same_topk=same_topk, peak_tops=peak8.value)
+                  gpu_launches=launches8, dacq=dacq, same_topk=same_topk, peak_tops=peak8.value,
+                  peak_burst_tops=peak8b.value)
 
     if rank != 0:
         if world > 1:
@@ -433,13 +437,16 @@ def run_gpu_arm(args):
             "max_abs_acq_difference_vs_dmma": i8["dacq"], "same_top_batch_as_dmma": i8["same_topk"],
             "roofline": {"kernel": "oz_sumsq_kernel", "bound": "tensor",
                          "achieved": 21.0 * i8["flops"] / (i8["ms"] * 1e-3) / 1e12 if i8["ms"] > 0 else None,
-                         "peak": i8["peak_tops"], "unit": "TOP/s (int8 multiply + add)",
+                         "peak": i8["peak_tops"], "peak_burst": i8["peak_burst_tops"],
+                         "unit": "TOP/s (int8 multiply + add)",
                          "frac": (21.0 * i8["flops"] / (i8["ms"] * 1e-3) / 1e12 / i8["peak_tops"])
                          if i8["ms"] > 0 and i8["peak_tops"] else None,
                          "fp64_equivalent_tflops": i8["flops"] / (i8["ms"] * 1e-3) / 1e12 if i8["ms"] > 0 else None,
                          "peak_source": "bo_i8_peak_tops: the kernel's own 21-MMA batch (kind::i8 128x64x32, A from "
-                                        "TMEM) on resident operands, one CTA per SM, ~30 ms, measured in this run "
-                                        "(MEASURED_PEAKS.json has no int8 entry; nominal B200 dense int8 4.5 POP/s)",
+                                        "TMEM) on resident operands, one CTA per SM, measured in this run: `peak` "
+                                        "sustained for 0.4 s (the contraction is timed inside long steps), "
+                                        "`peak_burst` for 30 ms (MEASURED_PEAKS.json has no int8 entry; nominal "
+                                        "B200 dense int8 4.5 POP/s)",
                          "algorithmic": "21 digit-pair products x m*N^2 multiply-adds per candidate",
                          "traffic": load_traffic("oz_traffic.json"),
                          "launches": i8["launches"], "avg_launch_ms": i8["ms"] / max(1, i8["launches"]),
