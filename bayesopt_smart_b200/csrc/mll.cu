@@ -117,95 +117,112 @@ __global__ void mll_sum_kernel(double* __restrict__ out, const double* __restric
 // Cholesky, forward substitution and the three MLL terms live in shared memory.  This is the shape of the
 // reference's own use (tens of evaluated points, hundreds of sequential Powell evaluations per iteration:
 // numba_kernels.py:305-315), where launch latency, not arithmetic, is the cost.
-constexpr int SMALL_N = 128;
+constexpr int SMALL_ROWS = 128;        // rows of the shared-memory matrix: n training rows + the target row
+constexpr int SMALL_N = SMALL_ROWS - 1;
 
-__global__ void __launch_bounds__(256)
-    mll_small_kernel(double* __restrict__ out, const double* __restrict__ x, int ldx, const double* __restrict__ y,
-                     int ldy, int n, int d, int m, ObjParams hp0, const double* __restrict__ ls_all,
-                     const double* __restrict__ jit_all) {
+// One CTA per (setting, objective); two threads per matrix row (columns of equal parity).  The standardised
+// targets ride along as row n of the matrix: a right-looking Cholesky leaves z = L^-1 yt in that row, so there is
+// no separate forward substitution.  Column j costs ONE barrier: the trailing update uses the unscaled column
+// and the pivot, a_ik -= a_ij a_kj / piv (the scaled column itself is never needed -- only its diagonal, for the
+// log-determinant, and its target-row entry, for the fit term).  The last CTA of a setting adds the per-objective
+// values in objective order (deterministic), so the whole evaluation is one launch.
+// Hyper-parameters of up to SMALL_INLINE settings travel in the kernel parameters (a Powell evaluation is one
+// setting: no host-to-device copies on that path).
+constexpr int SMALL_INLINE = 4;
+struct SmallHyper {
+  double ls[SMALL_INLINE * BO_MAX_OBJECTIVES];
+  double jit[SMALL_INLINE];
+};
+
+__global__ void __launch_bounds__(2 * SMALL_ROWS)
+    mll_small_kernel(double* __restrict__ out, double* __restrict__ vals, unsigned int* __restrict__ done,
+                     const double* __restrict__ x, int ldx, const double* __restrict__ y, int ldy, int n, int d, int m,
+                     ObjParams hp0, const double* __restrict__ ls_dev, const double* __restrict__ jit_dev,
+                     const __grid_constant__ SmallHyper inl) {
+  const double* ls_all = ls_dev ? ls_dev : inl.ls;
+  const double* jit_all = jit_dev ? jit_dev : inl.jit;
   extern __shared__ double sm[];
-  double(*A)[SMALL_N + 1] = reinterpret_cast<double(*)[SMALL_N + 1]>(sm);  // Gram / factor (lower)
-  double* xs = sm + SMALL_N * (SMALL_N + 1);                                // n x d coordinates
-  double* yt = xs + SMALL_N * BO_MAX_DIMS;                                  // standardised targets, then z
-  double* scratch = yt + SMALL_N;                                           // 8 doubles
+  double(*A)[SMALL_ROWS + 1] = reinterpret_cast<double(*)[SMALL_ROWS + 1]>(sm);  // rows 0..n-1: Gram; row n: targets
+  double* xs = sm + SMALL_ROWS * (SMALL_ROWS + 1);                                // n x d coordinates
+  double* rinv = xs + SMALL_ROWS * BO_MAX_DIMS;                                   // 1 / l_jj per column
+  double* scratch = rinv + SMALL_ROWS;                                            // 8 doubles
   __shared__ int nan_flag;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = blockIdx.x;
+  __shared__ unsigned int ticket;
+  const int tid = threadIdx.x;
+  const int row = tid >> 1, q = tid & 1;
+  const int s = blockIdx.x, o = blockIdx.y;
   const double jit = jit_all[s];
   if (tid == 0) nan_flag = 0;
-  for (int e = tid; e < n * d; e += 256) xs[e] = x[(long long)(e / d) * ldx + (e % d)];
-  __syncthreads();
-  double total = 0.0;
-  for (int o = 0; o < m; ++o) {
-    const double ls = ls_all[(long long)s * m + o];
-    const double coef = -0.5 / (ls * ls);
-    // ---- standardised targets (population std of y - mu0, skipped when 0: numba_kernels.py:201-208)
-    double acc = 0.0;
-    for (int i = tid; i < n; i += 256) acc += y[(long long)i * ldy + o] - hp0.prior_mean[o];
-    const double mean = block_sum(acc, scratch) / n;
-    acc = 0.0;
-    for (int i = tid; i < n; i += 256) {
-      const double c = (y[(long long)i * ldy + o] - hp0.prior_mean[o]) - mean;
-      acc = fma(c, c, acc);
-    }
-    const double sd = sqrt(block_sum(acc, scratch) / n);
-    for (int i = tid; i < n; i += 256) {
-      double c = y[(long long)i * ldy + o] - hp0.prior_mean[o];
-      if (sd > 0.0) c /= sd;
-      yt[i] = c;
-    }
-    // ---- correlation matrix + jitter, lower triangle
-    for (int e = tid; e < n * n; e += 256) {
-      const int i = e / n, j = e - i * n;
-      if (j > i) continue;
+  for (int e = tid; e < n * d; e += 2 * SMALL_ROWS) xs[e] = x[(long long)(e / d) * ldx + (e % d)];
+  // ---- standardised targets (population std of y - mu0, skipped when 0: numba_kernels.py:201-208)
+  double acc = 0.0;
+  for (int i = tid; i < n; i += 2 * SMALL_ROWS) acc += y[(long long)i * ldy + o] - hp0.prior_mean[o];
+  const double mean = block_sum(acc, scratch) / n;  // (block_sum synchronises: xs is visible afterwards)
+  acc = 0.0;
+  for (int i = tid; i < n; i += 2 * SMALL_ROWS) {
+    const double c = (y[(long long)i * ldy + o] - hp0.prior_mean[o]) - mean;
+    acc = fma(c, c, acc);
+  }
+  const double sd = sqrt(block_sum(acc, scratch) / n);
+  // ---- lower triangle of the correlation matrix + jitter; the target row
+  const double ls = ls_all[(long long)s * m + o];
+  const double coef = -0.5 / (ls * ls);
+  if (row < n) {
+    for (int k = q; k <= row; k += 2) {
       double sq = 0.0;
-      for (int k = 0; k < d; ++k) {
-        const double diff = xs[i * d + k] - xs[j * d + k];
+      for (int c = 0; c < d; ++c) {
+        const double diff = xs[row * d + c] - xs[k * d + c];
         sq = fma(diff, diff, sq);
       }
-      A[i][j] = rbf_exp(sq * coef, kExp2Tab) + (i == j ? jit : 0.0);
+      A[row][k] = rbf_exp(sq * coef, kExp2Tab) + (row == k ? jit : 0.0);
     }
-    // ---- Cholesky in place, one barrier per column; same pivot policy as potf2_kernel
-    const double neg_tol = 1.4901161193847656e-08 * (1.0 + jit);
-    double logdiag = 0.0;
-    for (int j = 0; j < n; ++j) {
-      __syncthreads();
-      double piv = A[j][j];
-      if (!(piv >= jit)) {
-        if (!(piv > -neg_tol) && tid == 0) nan_flag = 1;
-        piv = fmax(jit, 2.220446049250313e-16);
-      }
-      const double dsq = sqrt(piv);
-      logdiag += log(dsq);  // same value in every thread
-      __syncthreads();      // everybody has read A[j][j] and column j before it is rescaled
-      for (int i = j + tid; i < n; i += 256) A[i][j] = (i == j) ? dsq : A[i][j] / dsq;
-      __syncthreads();
-      const int rem = n - j - 1;
-      for (int e = tid; e < rem * rem; e += 256) {
-        const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-        if (k <= i) A[i][k] = fma(-A[i][j], A[k][j], A[i][k]);
-      }
+  } else if (row == n) {
+    for (int k = q; k < n; k += 2) {
+      double c = y[(long long)k * ldy + o] - hp0.prior_mean[o];
+      if (sd > 0.0) c /= sd;
+      A[n][k] = c;
     }
-    __syncthreads();
-    // ---- z = L^-1 yt by forward substitution (warp 0; lanes split the dot product)
-    if (warp == 0) {
-      for (int i = 0; i < n; ++i) {
-        double p = 0.0;
-        for (int k = lane; k < i; k += 32) p = fma(A[i][k], yt[k], p);
-#pragma unroll
-        for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-        if (lane == 0) yt[i] = (yt[i] - p) / A[i][i];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    acc = 0.0;
-    for (int i = tid; i < n; i += 256) acc = fma(yt[i], yt[i], acc);
-    const double fit = block_sum(acc, scratch);
-    total += -0.5 * fit - logdiag - 0.5 * n * log(2.0 * 3.14159265358979323846);
-    __syncthreads();
   }
-  if (tid == 0) out[s] = nan_flag ? __longlong_as_double(0x7ff8000000000000ll) : total;
+  // ---- right-looking Cholesky, one barrier per column; same pivot policy as potf2_kernel
+  const double neg_tol = 1.4901161193847656e-08 * (1.0 + jit);
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();  // the update of column j (by the previous step) is complete
+    double piv = A[j][j];
+    if (!(piv >= jit)) {
+      if (!(piv > -neg_tol) && tid == 0) nan_flag = 1;
+      piv = fmax(jit, 2.220446049250313e-16);
+    }
+    const double r = rsqrt(piv);  // 1 / l_jj, computed redundantly by every thread (no second barrier)
+    if (tid == 0) rinv[j] = r;
+    if (row > j && row <= n) {
+      const double l = A[row][j] * (r * r);  // a_ij / piv
+      const int kend = row < n ? row : n - 1;  // the target row has no diagonal entry
+      for (int k = j + 1 + ((j + 1 + q) & 1); k <= kend; k += 2) A[row][k] = fma(-l, A[k][j], A[row][k]);
+    }
+  }
+  __syncthreads();
+  // z_j = a_nj / l_jj;  log det L = -sum log(1 / l_jj)
+  double fit = 0.0, logdiag = 0.0;
+  for (int j = tid; j < n; j += 2 * SMALL_ROWS) {
+    const double z = A[n][j] * rinv[j];
+    fit = fma(z, z, fit);
+    logdiag -= log(rinv[j]);
+  }
+  fit = block_sum(fit, scratch);
+  logdiag = block_sum(logdiag, scratch);
+  if (tid == 0) {
+    const double v = -0.5 * fit - logdiag - 0.5 * n * log(2.0 * 3.14159265358979323846);
+    vals[(long long)s * m + o] = nan_flag ? __longlong_as_double(0x7ff8000000000000ll) : v;
+    __threadfence();
+    ticket = atomicInc(&done[s], (unsigned int)(m - 1));  // wraps to 0 after the m-th arrival: self-resetting
+  }
+  __syncthreads();
+  if (tid == 0 && ticket == (unsigned int)(m - 1)) {
+    __threadfence();
+    double total = 0.0;
+    for (int oo = 0; oo < m; ++oo) total += reinterpret_cast<volatile double*>(vals)[(long long)s * m + oo];
+    out[s] = total;  // NaN if any objective was not positive definite
+  }
 }
 
 }  // namespace
@@ -255,21 +272,36 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
   const int gs = group_settings(npad, m, n_settings);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   if (n <= SMALL_N) {
-    // one CTA per setting; hyper-parameters travel through the head of the workspace
+    // one CTA per (setting, objective); hyper-parameters, per-objective values and the arrival counters travel
+    // through the head of the workspace
     double* ls_dev = reinterpret_cast<double*>(ws);
     double* jit_small = ls_dev + (size_t)n_settings * m;
-    BO_CUDA(cudaMemcpyAsync(ls_dev, length_scales, sizeof(double) * n_settings * m, cudaMemcpyHostToDevice, stream));
-    BO_CUDA(cudaMemcpyAsync(jit_small, jitter, sizeof(double) * n_settings, cudaMemcpyHostToDevice, stream));
+    double* vals_small = jit_small + n_settings;
+    unsigned int* done = reinterpret_cast<unsigned int*>(vals_small + (size_t)n_settings * m);
+    SmallHyper inl;
+    memset(&inl, 0, sizeof(inl));
+    const bool inline_hyper = n_settings <= SMALL_INLINE;
+    if (inline_hyper) {
+      memcpy(inl.ls, length_scales, sizeof(double) * n_settings * m);
+      memcpy(inl.jit, jitter, sizeof(double) * n_settings);
+    } else {
+      BO_CUDA(cudaMemcpyAsync(ls_dev, length_scales, sizeof(double) * n_settings * m, cudaMemcpyHostToDevice, stream));
+      BO_CUDA(cudaMemcpyAsync(jit_small, jitter, sizeof(double) * n_settings, cudaMemcpyHostToDevice, stream));
+    }
+    BO_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int) * n_settings, stream));
     ObjParams hps;
     memset(&hps, 0, sizeof(hps));
     for (int o = 0; o < m; ++o) hps.prior_mean[o] = prior_mean[o];
-    const size_t smem = (size_t)(SMALL_N * (SMALL_N + 1) + SMALL_N * BO_MAX_DIMS + SMALL_N + 8) * sizeof(double);
+    const size_t smem =
+        (size_t)(SMALL_ROWS * (SMALL_ROWS + 1) + SMALL_ROWS * BO_MAX_DIMS + SMALL_ROWS + 8) * sizeof(double);
     static bool small_attr = false;
     if (!small_attr) {
       BO_CUDA(cudaFuncSetAttribute(mll_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       small_attr = true;
     }
-    mll_small_kernel<<<n_settings, 256, smem, stream>>>(out, x, ldx, y, ldy, n, d, m, hps, ls_dev, jit_small);
+    mll_small_kernel<<<dim3(n_settings, m), 2 * SMALL_ROWS, smem, stream>>>(
+        out, vals_small, done, x, ldx, y, ldy, n, d, m, hps, inline_hyper ? nullptr : ls_dev,
+        inline_hyper ? nullptr : jit_small, inl);
     BO_LAUNCH_CHECK("mll_small_kernel");
     BO_CUDA(cudaStreamSynchronize(stream));
     return BO_OK;
