@@ -156,9 +156,7 @@ __global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long stri
 // six 16-byte plane rows; the posterior-mean dot product k*.alpha is accumulated from the unquantised values.
 constexpr int OZK_ROWS = 256;
 constexpr int OZK_THREADS = 2 * OZ_TN;
-#ifndef OZK_MIN_CTAS
-#define OZK_MIN_CTAS 3
-#endif
+constexpr int OZK_MIN_CTAS = 3;  // 168 registers: 2 and 4 CTAs per SM were measured 0-8 % slower
 // row of the staged training block: D coordinates (D is even) then MOBJ alphas, padded to whole 16-byte pairs --
 // every lane of a warp reads the same row (broadcast), so the rows can be read with 16-byte loads
 __host__ __device__ constexpr int ozk_row_doubles(int d, int m) { return (d + m + 1) & ~1; }
