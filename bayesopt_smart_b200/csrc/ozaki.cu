@@ -55,10 +55,11 @@ constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_TN * size
 constexpr unsigned long long OZ_BIAS = 0x0000008080808080ull;  // 0x80 in each of the five low digit bytes
 constexpr double OZ_MAGIC = 6755399441055744.0;                // 1.5 * 2^52
 
-// bytes 0..5 of the result are the balanced digits (least significant first) of rint(v * scale)
-__device__ __forceinline__ unsigned long long balanced_digits(double v, double scale) {
+// bytes 0..5 of the result, with 0x80 XORed onto bytes 0..4, are the balanced digits (least significant first) of
+// rint(v * scale); the XOR is applied to whole plane rows by plane_row (one instruction per four digits)
+__device__ __forceinline__ unsigned long long biased_digits(double v, double scale) {
   const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(v, scale, OZ_MAGIC));
-  return (bits + OZ_BIAS) ^ OZ_BIAS;
+  return bits + OZ_BIAS;
 }
 
 // gather byte `BI` (0..5) of 16 digit words into one 16-byte row (byte b <-> word b)
@@ -75,6 +76,7 @@ __device__ __forceinline__ uint4 plane_row(const unsigned long long (&w)[16]) {
     const uint32_t t01 = __byte_perm(v[0], v[1], j | ((4 + j) << 4));
     const uint32_t t23 = __byte_perm(v[2], v[3], j | ((4 + j) << 4));
     out[q] = __byte_perm(t01, t23, 0x5410);
+    if (BI < 5) out[q] ^= 0x80808080u;  // biased byte -> balanced digit (the top digit, byte 5, carries no bias)
   }
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
@@ -139,7 +141,7 @@ __global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long stri
   for (int b = 0; b < 16; ++b) {
     const int k = k0 + b;
     const double w = (row < n && k <= row) ? W[wpack_index(row, k)] : 0.0;
-    dg[b] = balanced_digits(w, qs);
+    dg[b] = biased_digits(w, qs);
   }
   unsigned char* dst = wq + (long long)o * strideWq + blk * OZ_A_STAGE + rg * 256 + kc * 128 + r * 16;
   *reinterpret_cast<uint4*>(dst + 0 * OZ_A_PLANE) = plane_row<5>(dg);
@@ -243,9 +245,9 @@ __global__ void __launch_bounds__(OZK_THREADS, OZK_MIN_CTAS)
         unsigned long long dg[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-          const double e = rbf_exp(sq[b] * coef[o], exp_tab);
+          const double e = rbf_exp<false>(sq[b] * coef[o], exp_tab);
           macc[o] = fma(pvar[o] * e, xs[kb + b][D + o], macc[o]);
-          dg[b] = balanced_digits(e, kscale);
+          dg[b] = biased_digits(e, kscale);
         }
         unsigned char* dst = kq + (((long long)o * chunk_tiles + ct) * nk_tot + ks) * OZ_B_STAGE + rg * 256 +
                              kc * 128 + r * 16;

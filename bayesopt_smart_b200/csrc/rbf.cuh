@@ -38,7 +38,10 @@ static __device__ __constant__ double kExpCoef[6] = {
     92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12,
     1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
 
-// tab: 64 doubles 2^(j/64), in shared memory (hot kernel) or kExp2Tab itself (L1-cached global)
+// tab: 64 doubles 2^(j/64), in shared memory (hot kernel) or kExp2Tab itself (L1-cached global).
+// FLUSH = false skips the final flush to zero: inputs below -706 then return exp(-706) = 2.5e-307 instead of 0,
+// which is the same thing to a caller that quantises the result (ozaki.cu) and saves four instructions per call.
+template <bool FLUSH = true>
 __device__ __forceinline__ double rbf_exp(double x, const double* __restrict__ tab) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
   const double xc = fmax(x, -706.0);         // keeps n inside int range and the result normal
@@ -54,6 +57,7 @@ __device__ __forceinline__ double rbf_exp(double x, const double* __restrict__ t
   p = fma(p, r, 1.0);
   const double v = tab[n & 63] * p;
   const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+  if (!FLUSH) return scaled;
   return (x < -706.0) ? 0.0 : scaled;  // exp(x) < 2.5e-307 is flushed to zero (also maps NaN-free inputs only)
 }
 
