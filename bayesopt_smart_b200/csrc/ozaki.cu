@@ -56,29 +56,37 @@ constexpr unsigned long long OZ_BIAS = 0x0000008080808080ull;  // 0x80 in each o
 constexpr double OZ_MAGIC = 6755399441055744.0;                // 1.5 * 2^52
 
 // bytes 0..5 of the result, with 0x80 XORed onto bytes 0..4, are the balanced digits (least significant first) of
-// rint(v * scale); the XOR is applied to whole plane rows by plane_row (one instruction per four digits)
+// rint(v * scale); the XOR is applied to whole packed words by digit_planes (one instruction per four digits)
 __device__ __forceinline__ unsigned long long biased_digits(double v, double scale) {
   const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(v, scale, OZ_MAGIC));
   return bits + OZ_BIAS;
 }
 
-// gather byte `BI` (0..5) of 16 digit words into one 16-byte row (byte b <-> word b)
-template <int BI>
-__device__ __forceinline__ uint4 plane_row(const unsigned long long (&w)[16]) {
-  uint32_t out[4];
+// 16 biased digit words -> the six 16-byte plane rows (rows[p] = plane p, most significant first; byte b of a row
+// belongs to word b).  Per group of four words a 4x4 byte transpose of the low halves (8 byte-permutes) and a 2x4
+// one of the high halves (4), then the bias is removed from the five low planes with one XOR per packed word.
+__device__ __forceinline__ void digit_planes(const unsigned long long (&w)[16], uint4 (&rows)[OZ_PLANES]) {
+  uint32_t pw[OZ_PLANES][4];  // [byte index 0..5][group]
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      v[e] = BI < 4 ? (uint32_t)w[4 * q + e] : (uint32_t)(w[4 * q + e] >> 32);
-    constexpr int j = BI & 3;
-    const uint32_t t01 = __byte_perm(v[0], v[1], j | ((4 + j) << 4));
-    const uint32_t t23 = __byte_perm(v[2], v[3], j | ((4 + j) << 4));
-    out[q] = __byte_perm(t01, t23, 0x5410);
-    if (BI < 5) out[q] ^= 0x80808080u;  // biased byte -> balanced digit (the top digit, byte 5, carries no bias)
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t a = (uint32_t)w[4 * g], b = (uint32_t)w[4 * g + 1], c = (uint32_t)w[4 * g + 2],
+                   d = (uint32_t)w[4 * g + 3];
+    const uint32_t ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
+    const uint32_t cd_lo = __byte_perm(c, d, 0x5140), cd_hi = __byte_perm(c, d, 0x7362);
+    pw[0][g] = __byte_perm(ab_lo, cd_lo, 0x5410) ^ 0x80808080u;
+    pw[1][g] = __byte_perm(ab_lo, cd_lo, 0x7632) ^ 0x80808080u;
+    pw[2][g] = __byte_perm(ab_hi, cd_hi, 0x5410) ^ 0x80808080u;
+    pw[3][g] = __byte_perm(ab_hi, cd_hi, 0x7632) ^ 0x80808080u;
+    const uint32_t ah = (uint32_t)(w[4 * g] >> 32), bh = (uint32_t)(w[4 * g + 1] >> 32),
+                   ch = (uint32_t)(w[4 * g + 2] >> 32), dh = (uint32_t)(w[4 * g + 3] >> 32);
+    const uint32_t abh = __byte_perm(ah, bh, 0x5140), cdh = __byte_perm(ch, dh, 0x5140);
+    pw[4][g] = __byte_perm(abh, cdh, 0x5410) ^ 0x80808080u;
+    pw[5][g] = __byte_perm(abh, cdh, 0x7632);  // the top digit carries no bias
   }
-  return make_uint4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+  for (int p = 0; p < OZ_PLANES; ++p)
+    rows[p] = make_uint4(pw[OZ_PLANES - 1 - p][0], pw[OZ_PLANES - 1 - p][1], pw[OZ_PLANES - 1 - p][2],
+                         pw[OZ_PLANES - 1 - p][3]);
 }
 
 // ------------------------------------------------------------------------------------------- W digits
@@ -144,12 +152,10 @@ __global__ void oz_wdigits_kernel(unsigned char* __restrict__ wq, long long stri
     dg[b] = biased_digits(w, qs);
   }
   unsigned char* dst = wq + (long long)o * strideWq + blk * OZ_A_STAGE + rg * 256 + kc * 128 + r * 16;
-  *reinterpret_cast<uint4*>(dst + 0 * OZ_A_PLANE) = plane_row<5>(dg);
-  *reinterpret_cast<uint4*>(dst + 1 * OZ_A_PLANE) = plane_row<4>(dg);
-  *reinterpret_cast<uint4*>(dst + 2 * OZ_A_PLANE) = plane_row<3>(dg);
-  *reinterpret_cast<uint4*>(dst + 3 * OZ_A_PLANE) = plane_row<2>(dg);
-  *reinterpret_cast<uint4*>(dst + 4 * OZ_A_PLANE) = plane_row<1>(dg);
-  *reinterpret_cast<uint4*>(dst + 5 * OZ_A_PLANE) = plane_row<0>(dg);
+  uint4 rows[OZ_PLANES];
+  digit_planes(dg, rows);
+#pragma unroll
+  for (int p = 0; p < OZ_PLANES; ++p) *reinterpret_cast<uint4*>(dst + p * OZ_A_PLANE) = rows[p];
 }
 
 // ------------------------------------------------------------------------------------------- K* digits
@@ -251,12 +257,10 @@ __global__ void __launch_bounds__(OZK_THREADS, OZK_MIN_CTAS)
         }
         unsigned char* dst = kq + (((long long)o * chunk_tiles + ct) * nk_tot + ks) * OZ_B_STAGE + rg * 256 +
                              kc * 128 + r * 16;
-        *reinterpret_cast<uint4*>(dst + 0 * OZ_B_PLANE) = plane_row<5>(dg);
-        *reinterpret_cast<uint4*>(dst + 1 * OZ_B_PLANE) = plane_row<4>(dg);
-        *reinterpret_cast<uint4*>(dst + 2 * OZ_B_PLANE) = plane_row<3>(dg);
-        *reinterpret_cast<uint4*>(dst + 3 * OZ_B_PLANE) = plane_row<2>(dg);
-        *reinterpret_cast<uint4*>(dst + 4 * OZ_B_PLANE) = plane_row<1>(dg);
-        *reinterpret_cast<uint4*>(dst + 5 * OZ_B_PLANE) = plane_row<0>(dg);
+        uint4 rows[OZ_PLANES];
+        digit_planes(dg, rows);
+#pragma unroll
+        for (int p = 0; p < OZ_PLANES; ++p) *reinterpret_cast<uint4*>(dst + p * OZ_B_PLANE) = rows[p];
       }
     }
   }
