@@ -533,19 +533,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       while (fc.valid && fed < drain_end + 2) {
         const int stage = fed % OZ_STAGES;
         mbar_wait(&full[stage], (fed / OZ_STAGES) & 1);  // TMA has landed the stage
+        // the planes go to registers first: only the store into the A slot has to wait for the slot
+        const unsigned char* src = a_src + stage * OZ_A_STAGE;
+        uint4 lo[3], hi[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          lo[p] = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE);        // k 0..15 of the row
+          hi[p] = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE + 128);  // k 16..31
+        }
         if (fed >= 2) {
           const uint32_t j = fed - 2;  // the k-step that used this A slot: its MMAs signal empty[its stage]
           mbar_wait(&empty[j % OZ_STAGES], (j / OZ_STAGES) & 1);
           tc_fence_after();
         }
-        const unsigned char* src = a_src + stage * OZ_A_STAGE;
         const uint32_t dst = lane_base + OZ_ASLOT_COL + (fed & 1) * OZ_ASLOT_COLS + (half * 3) * (OZ_KS / 4);
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const uint4 lo = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE);        // k 0..15 of the row
-          const uint4 hi = *reinterpret_cast<const uint4*>(src + p * OZ_A_PLANE + 128);  // k 16..31
-          tmem_st8(dst + p * (OZ_KS / 4), lo, hi);
-        }
+        for (int p = 0; p < 3; ++p) tmem_st8(dst + p * (OZ_KS / 4), lo[p], hi[p]);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
