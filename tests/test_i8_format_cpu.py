@@ -78,3 +78,34 @@ def test_image_layout_roundtrip():
                     off = ((ks * f8.S + s) * (rows // 8) + r // 8) * 256 + (k // 16) * 128 + (r % 8) * 16 + k % 16
                     img[off] = dig[s, r, ks * f8.KS + k]
     assert np.array_equal(f8.planes_from_image(img, rows, nk), dig)
+
+
+def _row_block(t, r, nsplit):
+    """Python restatement of oz_row_block (ozaki.cu): serpentine dealing of row blocks to the CTAs of a tile."""
+    return t * nsplit + ((nsplit - 1 - r) if (t & 1) else r)
+
+
+def test_serpentine_row_block_dealing_is_a_balanced_partition():
+    for nb in (1, 2, 5, 8, 16, 32, 33, 128):
+        for nsplit in (1, 2, 3, 4, 7, 8):
+            if nsplit > nb:
+                continue
+            seen, ksteps = [], []
+            for r in range(nsplit):
+                mine, t = [], 0
+                while _row_block(t, r, nsplit) < nb:
+                    mine.append(_row_block(t, r, nsplit))
+                    t += 1
+                assert mine, (nb, nsplit, r)          # every CTA of a tile has work (nsplit <= nb)
+                seen += mine
+                ksteps.append(sum(4 * (ib + 1) for ib in mine))  # k-steps of 32: row block ib spans 4 (ib + 1)
+            assert sorted(seen) == list(range(nb))    # every row block exactly once
+            # loads differ by at most the k-steps of the two largest blocks (an odd tail round)
+            assert max(ksteps) - min(ksteps) <= 8 * nb, (nb, nsplit, ksteps)
+            assert all(k % 4 == 0 for k in ksteps)    # the two MMA issuers rely on even k-step counts per block
+
+
+def test_accumulator_bound_at_the_size_limit():
+    """|acc_g| <= (pairs in g) * 128 * 128 * N must stay below 2^31 for N = 16384 (OZ_MAX_N) and the widest group."""
+    assert 6 * 128 * 128 * 16384 < 2 ** 31
+    assert 6 * 128 * 128 * (16384 + 128 * 44) >= 2 ** 31  # ... and not by a wide margin: the limit is real
