@@ -48,7 +48,7 @@ UNIT = "candidates/s"
 
 # --------------------------------------------------------------------------------------- workload
 def make_workload(rank: int = 0):
-    from oracle.gp_oracle import make_training_set  # synthetic data generator only (not the checker)
+    from bayesopt_smart_b200.workloads import make_training_set  # input definition only (no hot-path arithmetic)
 
     w = WORKLOAD
     x, y, mu0, var0 = make_training_set(w["fn"], w["n"], w["d"], seed=0)

@@ -150,3 +150,15 @@ def test_exact_hvi_known_answers():
     f3 = np.array([[1.0, 1.0, 2.0], [2.0, 2.0, 1.0]])
     assert orc.hypervolume_3d(f3, ref3) == pytest.approx(4.0 + 1.0)
     assert orc.exact_hvi(np.array([[3.0, 3.0, 3.0]]), f3, ref3)[0] == pytest.approx(27.0 - 5.0)
+
+
+def test_workload_generators_match_the_oracle_copies():
+    """bayesopt_smart_b200.workloads (inputs of bench.py / tools) and the oracle's own generators are the same
+    functions: identical arrays for every BASELINE workload."""
+    from bayesopt_smart_b200 import workloads as wl
+
+    for name, n, d in (("zdt1", 64, 6), ("zdt2", 50, 10), ("dtlz2", 40, 8)):
+        a = orc.make_training_set(name, n, d, seed=3)
+        b = wl.make_training_set(name, n, d, seed=3)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)

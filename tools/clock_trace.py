@@ -12,7 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
-from oracle import gp_oracle as orc  # noqa: E402
+from bayesopt_smart_b200 import workloads as orc  # noqa: E402  (input definitions only)
 
 x, y, mu0, var0 = orc.make_training_set("zdt1", 1024, 6, seed=0)
 gp = DeviceGP()

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayesopt_smart_b200 import numba_kernels as nk  # noqa: E402
-from oracle import gp_oracle as orc  # noqa: E402
+from bayesopt_smart_b200 import workloads as orc  # noqa: E402  (input definitions only)
 
 for n in (64, 128, 129, 192, 256, 384, 512, 768, 1024, 2048):
     x, y, mu0, var0 = orc.make_training_set("zdt1", n, 6, seed=0)

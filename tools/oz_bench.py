@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayesopt_smart_b200 import _lib  # noqa: E402
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
-from oracle import gp_oracle as orc  # noqa: E402
+from bayesopt_smart_b200 import workloads as orc  # noqa: E402  (input definitions only)
 
 
 def timed(fn, reps, flush):

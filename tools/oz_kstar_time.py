@@ -12,7 +12,7 @@ from bayesopt_smart_b200 import _lib  # noqa: E402
 if os.environ.get("BO_LIB"):
     _lib.LIB_PATH = os.environ["BO_LIB"]
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
-from oracle import gp_oracle as orc  # noqa: E402
+from bayesopt_smart_b200 import workloads as orc  # noqa: E402  (input definitions only)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n_cand = int(sys.argv[2]) if len(sys.argv) > 2 else 75776

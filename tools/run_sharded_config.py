@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from bayesopt_smart_b200 import distributed as bd  # noqa: E402
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
 from bayesopt_smart_b200.pareto import _mask_against, pareto_mask_device  # noqa: E402
-from oracle import gp_oracle as orc  # noqa: E402
+from bayesopt_smart_b200 import workloads as orc  # noqa: E402  (input definitions only)
 
 CONFIGS = {"cfg3": dict(fn="zdt2", n=4096, d=10, m=2, ls=0.5, total=16_000_000, pareto=False),
            "cfg4": dict(fn="dtlz2", n=2048, d=8, m=3, ls=0.5, total=8_000_000, pareto=True),
