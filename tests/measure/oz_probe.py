@@ -1,12 +1,12 @@
 """GPU probe of the INT8 (Ozaki) variance engine, stage by stage, against NumPy restatements of the digit
-format and of the exact integer contraction.  Usage: python tools/oz_probe.py [n] [n_cand] [d] [m]"""
+format and of the exact integer contraction.  Usage: python tests/measure/oz_probe.py [n] [n_cand] [d] [m]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from bayesopt_smart_b200 import _lib  # noqa: E402
 from bayesopt_smart_b200.engine import DeviceGP, to_device  # noqa: E402
 from oracle import gp_oracle as orc  # noqa: E402

@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bayesopt_smart_b200 import _lib  # noqa: E402
 from bayesopt_smart_b200.engine import DeviceGP, device_info, to_device  # noqa: E402
