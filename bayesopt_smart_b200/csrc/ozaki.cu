@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     mbar_init(&a_ready[1], 8);
     mbar_init(&turn[0], 1);
     mbar_init(&turn[1], 1);
-    mbar_init(tmem_full, 1);
+    mbar_init(tmem_full, 2);  // one commit from each MMA warp (their last k-steps of the row block)
     mbar_init(tmem_empty, 8);
     mbar_fence_init();
   }
@@ -462,10 +462,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     // ===== two MMA issuers: warp 1 takes the even k-steps (A slot 0), warp 10 the odd ones (slot 1).  The
     // tensor pipe buffers about one instruction, so whatever an issuing thread does between two batches (the
     // a_ready wait, the fence, the commit: ~170 cycles) is a bubble -- unless the other issuer's batch is running
-    // meanwhile.  Issue order is serialised by a token: an issuer hands over after 17 of its 21 MMAs (the six
-    // that may overwrite, accumulate = 0 on the first k-step of a row block, come first), the pipe executes in
-    // issue order (verified exact over 400 alternating k-steps, tools/umma_probe3.cu), and integer accumulation
-    // commutes.  nk is a multiple of 4, so warp 1 always opens a row block and warp 10 always closes it.
+    // meanwhile.  Issue is handed back and forth by a token after 17 of the 21 MMAs of a batch.  Correctness does
+    // not depend on how the pipe orders the two threads' MMAs: the only non-commutative MMAs are the six that
+    // overwrite (accumulate = 0 on the first k-step of a row block, always warp 1 because nk is a multiple of 4)
+    // and warp 10 waits for THEIR completion before its first batch of the block; integer accumulation commutes;
+    // and both issuers commit to tmem_full (count 2), each for its own last k-step of the block.
     // The whole warp walks the schedule (warp-uniform control flow keeps the descriptors in uniform registers);
     // one elected lane issues. =====
     const uint32_t me = warp == 1 ? 0u : 1u;
@@ -482,6 +483,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           mbar_wait(&a_ready[me], (g >> 1) & 1);  // feeders saw full[stage] and filled this A slot
           tc_fence_after();
           if (g > 0) mbar_wait(&turn[me], ((g - 1) >> 1) & 1);  // the other issuer is 17 MMAs into k-step g-1
+          if (ks == 1) {
+            // second k-step of a row block: the overwriting MMAs of the first one (other issuer) must have
+            // COMPLETED, not merely been issued -- from here on every MMA of the block accumulates, and
+            // accumulation commutes, so nothing below depends on how the pipe orders the two threads' MMAs
+            mbar_wait(&empty[(g - 1) % OZ_STAGES], ((g - 1) / OZ_STAGES) & 1);
+            tc_fence_after();
+          }
           if (elect_one()) {
             const uint32_t b_lo = b_lo0 + stage * (OZ_B_STAGE >> 4);
             const uint32_t first = ks > 0 ? 1u : 0u;
@@ -499,7 +507,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
               }
             }
             umma_commit(&empty[stage]);  // frees the smem stage and this A slot once these MMAs have read them
-            if (ks == c.nk - 1) umma_commit(tmem_full);  // accumulators of this row block are complete
+            // each issuer reports the completion of its own last k-step of the row block
+            if (ks >= c.nk - 2) umma_commit(tmem_full);
           }
           __syncwarp();
         }
