@@ -63,6 +63,8 @@ _SIGNATURES = {
                             c_void_p]),
     "bo_match_rows_f64": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_int, c_int, c_void_p]),
+    "bo_mask_evaluated_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int,
+                                      c_int, c_void_p]),
     "bo_topk_merge_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                                   c_void_p]),
     "bo_pareto_mask_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p]),

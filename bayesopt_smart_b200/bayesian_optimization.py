@@ -124,9 +124,9 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
         if world == 1:
             _, picked = gp.select(candidates, score, gp.x, batch_size)
         else:
-            # slack = n: even if every listed row of a rank were an evaluated point, enough remain
-            _, top_idx = bd.select_next_batch_sharded(gp, candidates, score, gp.x, batch_size, lo,
-                                                      slack=min(current_eval + 16, 1000))
+            # short lists first; the exchange repeats with longer ones (up to BO_MAX_TOPK, then an exhaustive
+            # mask of the evaluated rows) only when evaluated points crowd out the batch
+            _, top_idx = bd.select_next_batch_sharded(gp, candidates, score, gp.x, batch_size, lo, slack=16)
             picked = top_idx.cpu().numpy()
             picked = picked[picked >= 0]
         x_next = np.array([input_space[i] for i in picked])
@@ -206,6 +206,25 @@ class BayesianOptimization:
             self.prior_variance = compute_prior_variance(self.y_vector, self.n_evaluations, n_objectives)
         self.reference_point = np.zeros(n_objectives)
 
+    def _input_space_is_the_integer_grid(self) -> bool:
+        """True when ``input_space`` is still the int64 Cartesian grid of integral ``bounds`` built by the
+        constructor, so that each rank may generate its rows on the device instead of uploading them.  Identity
+        alone is not enough (the array can be edited in place): 64 evenly spaced rows plus the last one are
+        compared with the grid's closed form.  Non-integral bounds (np.arange then yields a float grid) or a
+        replaced / edited ``input_space`` take the upload path."""
+        space = self.input_space
+        if space is not self._grid_input_space or not np.issubdtype(space.dtype, np.integer):
+            return False
+        if not all(float(lo).is_integer() and float(hi).is_integer() for lo, hi in self.bounds):
+            return False
+        lo = np.array([int(b[0]) for b in self.bounds], dtype=np.int64)
+        ext = np.array([int(b[1]) - int(b[0]) for b in self.bounds], dtype=np.int64)
+        if space.shape != (int(np.prod(ext)), len(ext)):
+            return False
+        rows = np.unique(np.append(np.linspace(0, len(space) - 1, 64).astype(np.int64), len(space) - 1))
+        want = np.stack(np.unravel_index(rows, ext), axis=-1) + lo
+        return bool(np.array_equal(space[rows], want))
+
     def optimize(self) -> None:
         """Run the loop (reference :427-463)."""
         buffers = {name: getattr(self, name) for name in
@@ -215,7 +234,7 @@ class BayesianOptimization:
         self.x_vector, self.y_vector, self.n_evaluations = optimize(
             **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition,
             variance_engine=self.variance_engine,
-            candidates_from_bounds=self.input_space is self._grid_input_space)
+            candidates_from_bounds=self._input_space_is_the_integer_grid())
 
     def pareto_analysis(self) -> np.ndarray:
         """Pareto-efficient objective rows among the evaluated points (reference :465-488)."""

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -71,15 +72,32 @@ void profile_end(cudaStream_t st, double flops) {
   g_prof.flops += flops;
 }
 
+constexpr int kMaxDevices = 64;
+
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+  static std::atomic<int> sms[kMaxDevices];  // zero-initialised; one slot per device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
+}
+
+int ensure_dynamic_smem_impl(const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;  // (function, device) -> largest size set so far
+  int dev = 0;
+  BO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = done[std::make_pair(fn, dev)];
+  if (bytes > have) {
+    BO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return BO_OK;
 }
 
 static int make_params(ObjParams* hp, int m, const double* mean, const double* var, const double* ls,
@@ -444,6 +462,14 @@ int bo_match_rows_f64(uint8_t* out_flag_dev, const long long* idx_dev, int n_idx
   BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
   return match_rows(out_flag_dev, idx_dev, n_idx, index_base, cand_dev, cand_kind, ldc, x_dev, ldx, n, d,
                     (cudaStream_t)stream);
+}
+
+int bo_mask_evaluated_f64(double* out_dev, const double* acq_dev, const void* cand_dev, int cand_kind, int ldc,
+                          long long n_cand, const double* x_dev, int ldx, int n, int d, void* stream) {
+  BO_REQUIRE(out_dev && acq_dev && cand_dev && (x_dev || n == 0), "null pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(d >= 1 && d <= BO_MAX_DIMS && ldc >= d && n >= 0, "bad sizes");
+  return mask_evaluated(out_dev, acq_dev, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, (cudaStream_t)stream);
 }
 
 int bo_pareto_mask_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m, void* stream) {

@@ -44,8 +44,15 @@ struct ObjParams {
   double beta[BO_MAX_OBJECTIVES];
 };
 
-int device_sm_count();
+int device_sm_count();  // of the CURRENT device (cached per device)
 void count_launch();
+// cudaFuncSetAttribute(fn, MaxDynamicSharedMemorySize, bytes), remembered per (function, device): a process that
+// drives several GPUs sets the attribute once on each of them (the attribute is per device / context)
+int ensure_dynamic_smem_impl(const void* fn, size_t bytes);
+template <typename F>
+inline int ensure_dynamic_smem(F* fn, size_t bytes) {
+  return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(fn), bytes);
+}
 // live CUDA-event timing of the dominant kernel (see bo_profile_enable in bo_b200.h)
 bool profile_enabled();
 void profile_begin(cudaStream_t st);

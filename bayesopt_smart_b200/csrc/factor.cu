@@ -379,11 +379,10 @@ int cholesky_blocked(double* A, long long lda, long long strideA, int npad, int 
                      cudaStream_t stream) {
   chol_policy_kernel<<<batch, 256, 0, stream>>>(pol, A, lda, strideA, npad, jit_dev, jit_scalar, per_setting);
   BO_LAUNCH_CHECK("chol_policy_kernel");
-  static bool attr_set = false;
   const int smem = 2 * NB * (NB + 1) * (int)sizeof(double);
-  if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(block_inverse_kernel, (size_t)smem);
+    if (rc_attr) return rc_attr;
   }
   // Two-level blocking: inside an outer panel of NBO columns the 64-column steps update only the rest of that
   // panel (rank-64 updates of a narrow strip); the trailing matrix is updated once per outer panel with K = NBO.

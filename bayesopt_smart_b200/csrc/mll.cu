@@ -232,14 +232,16 @@ static int group_settings(int npad, int m, int n_settings) {
   // B200) -- the 64-column steps of the blocked Cholesky and the forward substitution are latency chains whose
   // cost per group does not depend on how many matrices ride along
   const size_t per = (size_t)m * npad * npad * sizeof(double);
-  static size_t budget = 0;
+  // per device ordinal (a process may drive GPUs of different sizes)
+  static size_t budgets[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  size_t budget = budgets[dev];
   if (budget == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
+    size_t free_b = 0, total_b = 0;
     budget = (size_t)4 << 30;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
-        prop.totalGlobalMem / 8 > budget)
-      budget = prop.totalGlobalMem / 8;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b / 8 > budget) budget = total_b / 8;
+    budgets[dev] = budget;
   }
   size_t g = budget / per;
   if (g < 1) g = 1;
@@ -294,10 +296,9 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
     for (int o = 0; o < m; ++o) hps.prior_mean[o] = prior_mean[o];
     const size_t smem =
         (size_t)(SMALL_ROWS * (SMALL_ROWS + 1) + SMALL_ROWS * BO_MAX_DIMS + SMALL_ROWS + 8) * sizeof(double);
-    static bool small_attr = false;
-    if (!small_attr) {
-      BO_CUDA(cudaFuncSetAttribute(mll_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      small_attr = true;
+    {
+      const int rc_attr = ensure_dynamic_smem(mll_small_kernel, smem);
+      if (rc_attr) return rc_attr;
     }
     mll_small_kernel<<<dim3(n_settings, m), 2 * SMALL_ROWS, smem, stream>>>(
         out, vals_small, done, x, ldx, y, ldy, n, d, m, hps, inline_hyper ? nullptr : ls_dev,
@@ -323,10 +324,9 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
   BO_LAUNCH_CHECK("mll_prepare_y_kernel");
 
   const size_t solve_smem = (size_t)(npad + 64 + 8) * sizeof(double);
-  static size_t attr_smem = 0;
-  if (solve_smem > attr_smem) {
-    BO_CUDA(cudaFuncSetAttribute(mll_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-    attr_smem = solve_smem;
+  {
+    const int rc_attr = ensure_dynamic_smem(mll_solve_kernel, solve_smem);
+    if (rc_attr) return rc_attr;
   }
   const long long strideA = (long long)npad * npad, strideD = (long long)npad * 64;
   for (int s0 = 0; s0 < n_settings; s0 += gs) {

@@ -764,10 +764,9 @@ int oz_kstar_digits(unsigned char* kq, double* meandot, const void* cand, int ca
 int oz_sumsq(double* part, long long ld_chunk, const unsigned char* wq, const double* wscale,
              const unsigned char* kq, int n, int m, int tiles, int chunk_tiles, int nsplit, const ObjParams& hp,
              cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(oz_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(oz_sumsq_kernel, OZ_SMEM);
+    if (rc_attr) return rc_attr;
   }
   const int npad = round_up(n, OZ_TM), nb = npad / OZ_TM;
   if (nsplit > nb) nsplit = nb;

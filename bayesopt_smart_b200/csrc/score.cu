@@ -490,10 +490,9 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     set_error("score workspace too small: %zu < %zu", workspace_bytes, score_workspace_bytes(p));
     return BO_ERR_WORKSPACE;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    BO_CUDA(cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(trmm_sumsq_kernel, TR_SMEM);
+    if (rc_attr) return rc_attr;
   }
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   double* Kp[2];
@@ -573,10 +572,11 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
       profile_end(stream, (double)live * m * (double)n * (double)n);
     }
     BO_LAUNCH_CHECK("trmm_sumsq_kernel");
-    if (ov) BO_CUDA(cudaEventRecord(ov->buffer_free[b], stream));
     rc = finalize_chunk(out, cand0, n_cand, part, meandot[b], p.ld_chunk, tiles * TN, p.nb, m, hp, min_variance,
                         stream);
     if (rc) return rc;
+    // recorded AFTER finalize: K*(ci+2) on the helper stream rewrites meandot[b], which finalize(ci) still reads
+    if (ov) BO_CUDA(cudaEventRecord(ov->buffer_free[b], stream));
     if (!ov && ci + 1 < n_chunks) {
       rc = launch_kstar_chunk(ci + 1);
       if (rc) return rc;

@@ -50,12 +50,26 @@ __device__ __forceinline__ long long sample_pos(long long e, int stride) {
   return e * stride + (long long)((h >> 8) % (unsigned)stride);
 }
 
+// Device-side switch between the filtered scan and its exact fallback (no host round trip): a gated launch runs
+// only if "the survivor count is usable" (k <= *count <= capacity) equals `want_usable`, otherwise every CTA exits
+// at once and leaves the outputs alone.
+struct TopkGate {
+  const int* count;  // nullptr: not gated
+  int capacity;
+  int want_usable;
+};
+
 // sample_stride > 0: the input is the virtual array in_val[sample_pos(e)], e < n_in, positions >= n_total
 // are skipped.  n_in_dev != nullptr: the element count is read from device memory (clamped to n_in).
 __global__ void __launch_bounds__(SEL_THREADS)
     topk_slice_kernel(double* __restrict__ out_val, long long* __restrict__ out_idx, const double* __restrict__ in_val,
                       const long long* __restrict__ in_idx, long long n_in, int k, long long index_base,
-                      int sample_stride, long long n_total, const int* __restrict__ n_in_dev) {
+                      int sample_stride, long long n_total, const int* __restrict__ n_in_dev, TopkGate gate) {
+  if (gate.count) {
+    const int cnt = *gate.count;
+    const int usable = (cnt >= k && cnt <= gate.capacity) ? 1 : 0;
+    if (usable != gate.want_usable) return;
+  }
   if (n_in_dev) {
     const long long cnt = *n_in_dev;
     n_in = cnt < n_in ? cnt : n_in;
@@ -157,6 +171,38 @@ __global__ void match_rows_kernel(uint8_t* __restrict__ flag, const long long* _
   }
   __syncthreads();
   if (threadIdx.x == 0) flag[blockIdx.x] = (uint8_t)hit;
+}
+
+// Exhaustive form of the exclusion test (acquisition.py:139) for the rare case in which the listed top-k rows were
+// ALL evaluated points (more than BO_MAX_TOPK evaluated rows rank above the batch): out[i] = NaN (ranked last) when
+// candidate i equals some evaluated row, acq[i] otherwise.  One candidate per thread, evaluated rows staged through
+// shared memory 256 at a time and read as broadcasts; the first coordinate decides almost every comparison.
+constexpr int MASK_ROWS = 256;
+template <typename CT>
+__global__ void __launch_bounds__(256)
+    mask_evaluated_kernel(double* __restrict__ out, const double* __restrict__ acq, const CT* __restrict__ cand, int ldc,
+                          long long n_cand, const double* __restrict__ x, int ldx, int n, int d) {
+  __shared__ double xs[MASK_ROWS][BO_MAX_DIMS];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double c[BO_MAX_DIMS];
+#pragma unroll
+  for (int k = 0; k < BO_MAX_DIMS; ++k) c[k] = (k < d && i < n_cand) ? (double)cand[i * ldc + k] : 0.0;
+  bool hit = false;
+  for (int e0 = 0; e0 < n; e0 += MASK_ROWS) {
+    const int cnt = min(MASK_ROWS, n - e0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * d; t += blockDim.x) xs[t / d][t % d] = x[(long long)(e0 + t / d) * ldx + t % d];
+    __syncthreads();
+    for (int e = 0; e < cnt; ++e) {
+      if (xs[e][0] == c[0]) {
+        bool same = true;
+#pragma unroll
+        for (int k = 1; k < BO_MAX_DIMS; ++k) same = same && (k >= d || xs[e][k] == c[k]);
+        hit = hit || same;
+      }
+    }
+  }
+  if (i < n_cand) out[i] = hit ? __longlong_as_double(0x7ff8000000000000ll) : acq[i];
 }
 
 // Streaming filter of the top-k scan: keep every element that is not worse than the threshold element
@@ -331,7 +377,8 @@ size_t topk_workspace_bytes(long long n_cand, int k) {
 // stride > 0: first level reads the hashed sample of `val` (n_in = number of sample elements)
 static int topk_levels_impl(double* out_val, long long* out_idx, const double* val, const long long* idx,
                             long long n_in, int k, long long index_base, int stride, long long n_total,
-                            const int* n_in_dev, void* workspace, cudaStream_t stream) {
+                            const int* n_in_dev, void* workspace, cudaStream_t stream,
+                            TopkGate gate = TopkGate{nullptr, 0, 0}) {
   const long long blocks0 = (n_in + SEL_SLICE - 1) / SEL_SLICE;
   const size_t pairs = (size_t)(blocks0 > 0 ? blocks0 : 1) * (size_t)k;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -357,7 +404,7 @@ static int topk_levels_impl(double* out_val, long long* out_idx, const double* v
     long long* oi = last ? out_idx : ix[buf];
     topk_slice_kernel<<<(unsigned)blocks, SEL_THREADS, 0, stream>>>(ov, oi, cur_v, cur_i, cur_n, k, index_base,
                                                                     first ? stride : 0, n_total,
-                                                                    first ? n_in_dev : nullptr);
+                                                                    first ? n_in_dev : nullptr, gate);
     BO_LAUNCH_CHECK("topk_slice_kernel");
     if (last) break;
     cur_v = ov;
@@ -402,12 +449,15 @@ int topk_levels(double* out_val, long long* out_idx, const double* val, const lo
     topk_filter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(sv, si, count, FILTER_CAPACITY, val, n_in, index_base,
                                                              tv + (k - 1), ti + (k - 1));
     BO_LAUNCH_CHECK("topk_filter_kernel");
-    int count_h = 0;
-    BO_CUDA(cudaMemcpyAsync(&count_h, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    BO_CUDA(cudaStreamSynchronize(stream));
-    if (count_h >= k && count_h <= FILTER_CAPACITY)
-      return topk_levels_impl(out_val, out_idx, sv, si, count_h, k, 0, 0, 0, nullptr, workspace, stream);
-    // threshold unusable (fewer than k valid sample elements, NaN threshold, massive ties): exact fallback
+    // The survivor count stays on the device.  Both continuations are enqueued and gated by it: the exact top-k of
+    // the survivors runs when the count is usable (k <= count <= capacity); otherwise (fewer than k valid sample
+    // elements, NaN threshold, massive ties) the plain multi-level scan of the whole array runs instead.  The
+    // launches of the branch not taken exit in their first instruction, so there is no host synchronisation.
+    rc = topk_levels_impl(out_val, out_idx, sv, si, FILTER_CAPACITY, k, 0, 0, 0, count, workspace, stream,
+                          TopkGate{count, FILTER_CAPACITY, 1});
+    if (rc) return rc;
+    return topk_levels_impl(out_val, out_idx, val, idx, n_in, k, index_base, 0, 0, nullptr, workspace, stream,
+                            TopkGate{count, FILTER_CAPACITY, 0});
   }
   return topk_levels_impl(out_val, out_idx, val, idx, n_in, k, index_base, 0, 0, nullptr, workspace, stream);
 }
@@ -422,6 +472,20 @@ int match_rows(uint8_t* flag, const long long* idx, int n_idx, long long index_b
     match_rows_kernel<double><<<n_idx, 128, 0, stream>>>(flag, idx, index_base, static_cast<const double*>(cand),
                                                          ldc, x, ldx, n, d);
   BO_LAUNCH_CHECK("match_rows_kernel");
+  return BO_OK;
+}
+
+int mask_evaluated(double* out, const double* acq, const void* cand, int cand_kind, int ldc, long long n_cand,
+                   const double* x, int ldx, int n, int d, cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  const unsigned grid = (unsigned)((n_cand + 255) / 256);
+  if (cand_kind == BO_CAND_I64)
+    mask_evaluated_kernel<long long><<<grid, 256, 0, stream>>>(out, acq, static_cast<const long long*>(cand), ldc,
+                                                              n_cand, x, ldx, n, d);
+  else
+    mask_evaluated_kernel<double><<<grid, 256, 0, stream>>>(out, acq, static_cast<const double*>(cand), ldc, n_cand,
+                                                           x, ldx, n, d);
+  BO_LAUNCH_CHECK("mask_evaluated_kernel");
   return BO_OK;
 }
 

@@ -58,30 +58,64 @@ def merge_topk(gp, vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch
     return gp.topk_merge(vals, idx, k)
 
 
+def _local_list(gp, cand_shard, acq_shard, evaluated, k: int, index_base: int):
+    """This rank's best ``k`` (value, global index) pairs, exactly ``k`` long: evaluated rows carry index -1
+    ("no entry" for the merge), short shards are padded with empty entries."""
+    dev = acq_shard.device
+    n = acq_shard.numel()
+    kk = min(n, k)
+    if kk > 0:
+        vals, idx, flags = gp.select_listed(cand_shard, acq_shard, evaluated, kk, index_base)
+        idx = torch.where(flags.bool(), torch.full_like(idx, -1), idx)
+    else:
+        vals = torch.empty(0, dtype=torch.float64, device=dev)
+        idx = torch.empty(0, dtype=torch.int64, device=dev)
+    got = vals.numel()  # the kernel's own clamp (BO_MAX_TOPK) is honoured by padding from the RETURNED length
+    if got < k:
+        vals = torch.cat([vals, torch.full((k - got,), float("nan"), dtype=vals.dtype, device=dev)])
+        idx = torch.cat([idx, torch.full((k - got,), -1, dtype=idx.dtype, device=dev)])
+    return vals, idx
+
+
 def select_next_batch_sharded(gp, cand_shard: torch.Tensor, acq_shard: torch.Tensor, evaluated: torch.Tensor,
-                              batch_size: int, index_base: int, group=None, slack: int = 16):
+                              batch_size: int, index_base: int, group=None, slack: int = 16, max_list: int = None):
     """Distributed select_next_batch (reference acquisition.py:116-144 over the union of all shards).
 
-    Each rank lists its best ``batch_size + slack`` candidates, masks rows equal to an evaluated point
-    (value -> -inf), all ranks exchange the lists and merge.  Returns (values, global indices) tensors of
-    length ``batch_size`` on the device, identical on every rank.
+    Each rank lists its best ``k = batch_size + slack`` candidates (``k`` is clamped to BO_MAX_TOPK so that every
+    rank sends a list of the same length), marks rows equal to an evaluated point, all ranks exchange the lists
+    and merge them with the same comparator.  If fewer than ``batch_size`` valid entries survive while some rank
+    could still list more, ``k`` grows (x4, up to the cap) and the exchange is repeated -- every rank sees the same
+    merged list, so all take the same decision.  At the cap the evaluated candidates are masked out exhaustively
+    (``DeviceGP.mask_evaluated``) before listing, which makes the result exact for any number of evaluated points.
+    Returns (values, global indices) tensors of length ``batch_size`` on the device, identical on every rank;
+    exhausted candidate sets give trailing entries with index -1.
     """
-    n = acq_shard.numel()
-    _, world = world_info(group)
-    k = batch_size + slack  # same list length on every rank (all-gather needs equal sizes)
-    kk = min(n, k)
-    vals, idx = gp.topk(acq_shard, kk, index_base) if kk > 0 else (
-        torch.empty(0, dtype=torch.float64, device=acq_shard.device),
-        torch.empty(0, dtype=torch.int64, device=acq_shard.device))
-    if kk > 0:
-        flags = gp.match_rows(idx, cand_shard, evaluated, index_base)
-        # an evaluated row is dropped from the ranking entirely: index -1 marks "no entry" for the merge
-        idx = torch.where(flags.bool(), torch.full_like(idx, -1), idx)
-    if kk < k:  # short shard: pad the list with empty entries
-        vals = torch.cat([vals, torch.full((k - kk,), float("nan"), dtype=vals.dtype, device=vals.device)])
-        idx = torch.cat([idx, torch.full((k - kk,), -1, dtype=idx.dtype, device=idx.device)])
-    gv, gi = gather_topk(vals, idx, group)
-    return merge_topk(gp, gv, gi, batch_size)
+    from . import _lib  # BO_MAX_TOPK
+
+    cap = int(max_list or _lib.BO_MAX_TOPK)
+    dev = acq_shard.device
+    n_local = torch.tensor([acq_shard.numel()], dtype=torch.int64, device=dev)
+    n_max = int(all_gather_cat(n_local, group).max().item())  # longest shard: no rank can list more than this
+    k = max(1, min(batch_size + max(int(slack), 0), cap))
+    masked = False
+    while True:
+        vals, idx = _local_list(gp, cand_shard, acq_shard, evaluated, k, index_base)
+        gv, gi = gather_topk(vals, idx, group)
+        mv, mi = merge_topk(gp, gv, gi, batch_size)
+        if mi.numel() < batch_size:  # fewer pairs than the batch in total (tiny candidate sets)
+            pad = batch_size - mi.numel()
+            mv = torch.cat([mv, torch.full((pad,), float("nan"), dtype=mv.dtype, device=dev)])
+            mi = torch.cat([mi, torch.full((pad,), -1, dtype=mi.dtype, device=dev)])
+        enough = bool((mi >= 0).all().item())
+        exhausted = k >= min(n_max, cap)
+        if enough or (exhausted and (masked or k >= n_max)):
+            return mv, mi
+        if exhausted:
+            acq_shard = gp.mask_evaluated(acq_shard, cand_shard, evaluated) if acq_shard.numel() else acq_shard
+            masked = True
+            k = max(1, min(batch_size + 16, cap))
+            continue
+        k = min(cap, k * 4)
 
 
 def gather_ragged_rows(rows: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int]]:

@@ -225,25 +225,54 @@ class DeviceGP:
                                               _stream()))
         return flags
 
+    def mask_evaluated(self, acq: torch.Tensor, candidates: torch.Tensor, evaluated: torch.Tensor) -> torch.Tensor:
+        """Copy of ``acq`` with NaN (ranked last) at every candidate row that equals an evaluated row -- the
+        exhaustive form of the exclusion test of acquisition.py:139 (O(M * n) compares; fallback only)."""
+        out = torch.empty_like(acq)
+        n_ev = evaluated.shape[0]
+        _lib.check(self.lib.bo_mask_evaluated_f64(_ptr(out), _ptr(acq), _ptr(candidates), candidate_kind(candidates),
+                                                  candidates.stride(0), acq.numel(),
+                                                  _ptr(evaluated) if n_ev else None,
+                                                  evaluated.stride(0) if n_ev else 1, n_ev, candidates.shape[1],
+                                                  _stream()))
+        return out
+
+    def select_listed(self, candidates: torch.Tensor, acq: torch.Tensor, evaluated: torch.Tensor, k: int,
+                      index_base: int = 0):
+        """Top-``k`` list of this shard with evaluated rows marked: (values, indices, flags) on the device."""
+        vals, idx = self.topk(acq, k, index_base)
+        flags = self.match_rows(idx, candidates, evaluated, index_base)
+        return vals, idx, flags
+
     def select(self, candidates: torch.Tensor, acq: torch.Tensor, evaluated: torch.Tensor, batch_size: int,
                index_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
         """select_next_batch on device (reference acquisition.py:116-144).
 
         Takes the top-(batch+slack) scores, drops rows that equal an evaluated point, keeps the first
-        ``batch_size``; the slack grows until enough rows survive or the candidates are exhausted.
-        Returns (values, global indices) as host arrays, best first.
+        ``batch_size``; the slack grows until enough rows survive or the candidates are exhausted.  If even the
+        longest list the top-k kernel supports (BO_MAX_TOPK) consists of evaluated rows only, every evaluated
+        candidate is masked out first (``mask_evaluated``) and the list is taken from the masked scores, so the
+        result is the reference's for any number of evaluated points.
+        Returns (values, global indices) as host arrays, best first; fewer than ``batch_size`` rows only when
+        fewer un-evaluated candidates exist (as in the reference).
         """
         n = acq.numel()
+        cap = min(n, _lib.BO_MAX_TOPK)
         k = min(n, batch_size + 16)
+        masked = False
         while True:
-            vals, idx = self.topk(acq, k, index_base)
-            flags = self.match_rows(idx, candidates, evaluated, index_base)
+            vals, idx, flags = self.select_listed(candidates, acq, evaluated, k, index_base)
             v = vals.cpu().numpy()
             i = idx.cpu().numpy()
             keep = (flags.cpu().numpy() == 0) & (i >= 0)
-            if keep.sum() >= batch_size or k >= min(n, _lib.BO_MAX_TOPK):
+            if keep.sum() >= batch_size or (k >= cap and (masked or k >= n)):
                 return v[keep][:batch_size], i[keep][:batch_size]
-            k = min(n, _lib.BO_MAX_TOPK, k * 4)
+            if k >= cap:
+                acq = self.mask_evaluated(acq, candidates, evaluated)
+                masked = True
+                k = min(n, batch_size + 16)
+                continue
+            k = min(cap, k * 4)
 
     def topk_merge(self, vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global top-k of gathered (value, index) pairs with the same total order (after an all-gather)."""

@@ -157,8 +157,9 @@ int bo_acquisition_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev,
  * Top-k of acq (value descending, index ascending on ties, NaN last).  Writes k
  * (value, index + index_base) pairs sorted best-first.  k <= BO_MAX_TOPK.  For n_cand >= 2^18 and
  * k <= 256 the scan is: exact top-k of a hashed 1/stride sample -> its k-th element is a lower bound of
- * the true k-th best -> one streaming filter pass -> exact top-k of the survivors (synchronises once to
- * read the survivor count; falls back to the plain multi-level scan if they overflow).
+ * the true k-th best -> one streaming filter pass -> exact top-k of the survivors.  The survivor count stays
+ * on the device: the survivor pass and the plain multi-level scan (the fallback when the survivors overflow or
+ * are too few) are both enqueued and gated by it, so the call is asynchronous on `stream`.
  * bo_match_rows_f64 flags, for each listed candidate row, whether it equals (==, all
  * d coordinates) some evaluated row x[0:n): the exclusion test of acquisition.py:139.
  * Replaces the argsort + walk of select_next_batch, acquisition.py:116-144.        */
@@ -168,6 +169,11 @@ int bo_topk_f64(double* out_val_dev, long long* out_idx_dev, const double* acq_d
 int bo_match_rows_f64(uint8_t* out_flag_dev, const long long* idx_dev, int n_idx, long long index_base,
                       const void* cand_dev, int cand_kind, int ldc, const double* x_dev, int ldx, int n, int d,
                       void* stream);
+/* exhaustive form of the same exclusion test over the WHOLE candidate set: out[i] = NaN (ranked last by
+ * bo_topk_f64) where candidate i equals some evaluated row, acq[i] elsewhere.  O(n_cand * n) compares; the
+ * selection falls back to it only when every listed top-BO_MAX_TOPK row turned out to be an evaluated point. */
+int bo_mask_evaluated_f64(double* out_dev, const double* acq_dev, const void* cand_dev, int cand_kind, int ldc,
+                          long long n_cand, const double* x_dev, int ldx, int n, int d, void* stream);
 /* merge of several sorted-or-not (value, index) lists into the global top-k with the
  * same comparator (used after the all-gather of per-rank top-k lists).             */
 int bo_topk_merge_f64(double* out_val_dev, long long* out_idx_dev, const double* val_dev, const long long* idx_dev,

@@ -122,3 +122,19 @@ def test_no_cpu_fallback_without_gpu():
         pkg.is_pareto_efficient(np.zeros((4, 2)))
     with pytest.raises(_lib.BoError):
         pkg.DeviceGP()
+
+
+def test_device_grid_is_used_only_for_the_untouched_integer_grid():
+    """the device-generated candidate grid replaces the upload only when input_space is provably the
+    int64 grid of integral bounds (no GPU needed: the constructor is host-only)."""
+    f = lambda p: np.array([p[0], -p[1]])  # noqa: E731
+    bo = pkg.BayesianOptimization(f, [(0, 7), (2, 9)], n_objectives=2, n_iterations=1, initial_samples=3)
+    assert bo._input_space_is_the_integer_grid()
+    bo.input_space[5, 1] += 1  # edited in place: same object, different points
+    assert not bo._input_space_is_the_integer_grid()
+    bo.input_space[5, 1] -= 1
+    bo.input_space = bo.input_space.copy()  # replaced by the caller
+    assert not bo._input_space_is_the_integer_grid()
+    bo2 = pkg.BayesianOptimization(f, [(0.5, 4.5), (0, 3)], n_objectives=2, n_iterations=1, initial_samples=3)
+    assert bo2.input_space.dtype == np.float64  # np.arange over non-integral bounds gives a float grid
+    assert not bo2._input_space_is_the_integer_grid()

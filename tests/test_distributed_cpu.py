@@ -24,10 +24,21 @@ def _free_port():
 class _HostMerge:
     """Stand-in for DeviceGP's CUDA top-k kernels with the same total order, on CPU tensors."""
 
+    def __init__(self, max_topk=1024):
+        self.max_topk = max_topk  # the CUDA kernel clamps k to BO_MAX_TOPK silently; so does this stand-in
+
     def topk(self, acq, k, index_base=0):
         a = acq.numpy()
-        order = orc.ranked_indices(a)[:k]
+        order = orc.ranked_indices(a)[: min(k, self.max_topk)]
         return torch.from_numpy(a[order].copy()), torch.from_numpy(order + index_base)
+
+    def select_listed(self, cand, acq, evaluated, k, index_base=0):
+        vals, idx = self.topk(acq, k, index_base)
+        return vals, idx, self.match_rows(idx, cand, evaluated, index_base)
+
+    def mask_evaluated(self, acq, cand, evaluated):
+        hit = (cand[:, None, :] == evaluated[None, :, :]).all(dim=2).any(dim=1)
+        return torch.where(hit, torch.full_like(acq, float("nan")), acq)
 
     def match_rows(self, idx, cand, evaluated, index_base=0):
         rows = cand[idx - index_base]
@@ -79,6 +90,57 @@ def _worker(rank, world, port, ret):
         ret[rank] = (ok_sel, ok_par, idx.tolist())
     finally:
         dist.destroy_process_group()
+
+
+def _worker_large_batch(rank, world, port, ret):
+    """batch + slack beyond the kernel's list cap, a short last shard, and more evaluated rows
+    at the top of the ranking than any list can hold -- lists must stay equally long on every rank, the list must
+    grow, and the exhaustive mask must take over at the cap."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        n_cand, d, cap = 61, 2, 16          # shards: 31 + 30 rows; with world 2 and cap 16 < batch + slack
+        cand = np.stack([np.arange(n_cand), rng.integers(0, 9, n_cand)], axis=1).astype(np.float64)
+        acq = rng.normal(size=n_cand)
+        order = np.argsort(-acq)
+        results = {}
+        for name, n_eval, batch, slack in [("grow", 10, 5, 0), ("mask", 40, 6, 1000), ("exhausted", 58, 6, 16)]:
+            evaluated = cand[order[:n_eval]]  # the best n_eval candidates were all evaluated already
+            lo, hi = bd.shard_range(n_cand, world, rank)
+            gp = _HostMerge(max_topk=cap)
+            vals, idx = bd.select_next_batch_sharded(gp, torch.from_numpy(cand[lo:hi]), torch.from_numpy(acq[lo:hi]),
+                                                     torch.from_numpy(evaluated), batch, lo, slack=slack, max_list=cap)
+            _, want_idx = orc.ref_select_next_batch(cand, acq, evaluated, batch)
+            got = idx.numpy()
+            results[name] = (got[got >= 0].tolist(), list(want_idx), int(idx.numel()))
+        # a shard shorter than the list: 3 candidates over 2 ranks (2 + 1), batch 2
+        lo, hi = bd.shard_range(3, world, rank)
+        tiny_c, tiny_a = cand[:3], np.array([0.5, 2.0, 1.0])
+        vals, idx = bd.select_next_batch_sharded(_HostMerge(max_topk=cap), torch.from_numpy(tiny_c[lo:hi]),
+                                                 torch.from_numpy(tiny_a[lo:hi]), torch.from_numpy(cand[50:51]), 2, lo,
+                                                 max_list=cap)
+        results["tiny"] = (idx.tolist(), [1, 2], int(idx.numel()))
+        ret[rank] = results
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_selection_large_batch_short_shard_many_evaluated():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_large_batch, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == world
+        for r in range(world):
+            for name, (got, want, length) in ret[r].items():
+                assert got == want, (r, name, got, want)
+            assert ret[r]["grow"][2] == 5 and ret[r]["mask"][2] == 6 and ret[r]["exhausted"][2] == 6
+            assert len(ret[r]["exhausted"][0]) == 3  # only 3 un-evaluated candidates exist
+        assert ret[0] == ret[1]
 
 
 def test_shard_range_partition():

@@ -162,11 +162,19 @@ def test_fused_path_matches_reference(pkg, golden, case):
     assert np.abs(out["acq"].cpu().numpy() - g["acq"]).max() <= bound
     far = np.all(g["std_var"] > 1e-6, axis=0)
     assert np.abs(out["acq"].cpu().numpy() - g["acq"])[far].max() <= 1e3 * m * tau
-    # the reference's top gaps are far larger than the bound: bit-exact selection
-    ref_sorted = np.sort(g["acq"])[::-1]
-    vals, idx = gp.select(to_device(cand), out["acq"], to_device(x[:n]), int(g["batch_size"]))
+    # Bit-exact selection is only claimed where it is provable: every gap of the REFERENCE's ranking that the
+    # selection crosses (between consecutive picks, and between the last pick and the runner-up) must exceed twice
+    # the largest score difference actually observed between the two implementations -- then no rounding
+    # difference can reorder them.  The gap condition is asserted, not assumed.
+    acq_dev = out["acq"].cpu().numpy()
+    b = int(g["batch_size"])
+    seen = {tuple(r) for r in np.asarray(x[:n], dtype=np.float64)}
+    order = [i for i in np.argsort(-g["acq"], kind="stable") if tuple(np.asarray(cand[i], dtype=np.float64)) not in seen]
+    ranked = g["acq"][order[: b + 1]]
+    observed = np.abs(acq_dev - g["acq"]).max()
+    assert np.min(-np.diff(ranked)) > 2.0 * observed, (np.diff(ranked), observed)
+    vals, idx = gp.select(to_device(cand), out["acq"], to_device(x[:n]), b)
     x_next = np.array([cand[i] for i in idx])
-    assert np.min(-np.diff(ref_sorted[: int(g["batch_size"]) + 2])) > 10 * bound or True
     assert np.array_equal(x_next, g["x_next"])
 
 
@@ -217,7 +225,9 @@ def test_cfg1_ill_conditioned_iterations_do_not_fail(pkg, golden):
             assert var.min().item() >= 1e-10 and var.max().item() <= hp[2 + o] * (1 + 1e-9)
         _, idx = gp.select(cand, out["acq"], to_device(g["x_vector"][: int(n)]), 3)
         assert len(idx) == 3
-    assert clamped >= 0
+    # at cond ~ 1e15 some iterations do need the clamp; the count is surfaced (bo_last_clamped_pivots) and small
+    print("clamped pivots over the 20 cfg1 iterations:", clamped)
+    assert clamped <= 4 * len(g["iteration"]), clamped
 
 
 # ------------------------------------------------------------------ fused path vs the oracle at larger sizes
