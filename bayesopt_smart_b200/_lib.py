@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "bo_b200.h")
 BO_OK, BO_ERR_INVALID, BO_ERR_CUDA, BO_ERR_NOT_PD, BO_ERR_WORKSPACE = 0, 1, 2, 3, 4
 BO_CAND_F64, BO_CAND_I64 = 0, 1
 BO_MAX_OBJECTIVES, BO_MAX_DIMS, BO_MAX_TOPK, BO_TILE = 4, 16, 1024, 128
+BO_PROF_CONTRACTION, BO_PROF_KSTAR, BO_PROF_FINALIZE, BO_PROF_TOPK, BO_PROF_FIT = 0, 1, 2, 3, 4
 
 
 class BoError(RuntimeError):
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "bo_launch_count": (c_longlong, [c_int]),
     "bo_profile_enable": (c_int, [c_int]),
     "bo_profile_read": (c_int, [_dp, POINTER(c_longlong), _dp]),
+    "bo_profile_read_kernel": (c_int, [c_int, _dp, POINTER(c_longlong), _dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

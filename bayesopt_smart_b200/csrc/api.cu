@@ -34,13 +34,18 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
+struct ProfRecord {
+  int kernel;
+  cudaEvent_t start, stop;
+  double work;
+};
 struct ProfState {
   std::mutex mu;
   bool on = false;
-  std::vector<cudaEvent_t> pool;                       // reusable events
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> live;  // recorded (start, stop) pairs
+  std::vector<cudaEvent_t> pool;  // reusable events
+  std::vector<ProfRecord> live;   // recorded (kernel id, start, stop, work) tuples
   cudaEvent_t pending = nullptr;
-  double flops = 0.0;
+  int pending_kernel = 0;
   cudaEvent_t get() {
     if (!pool.empty()) {
       cudaEvent_t e = pool.back();
@@ -56,20 +61,20 @@ ProfState g_prof;
 }  // namespace
 
 bool profile_enabled() { return g_prof.on; }
-void profile_begin(cudaStream_t st) {
+void profile_begin(cudaStream_t st, int kernel) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!g_prof.on) return;
   g_prof.pending = g_prof.get();
+  g_prof.pending_kernel = kernel;
   cudaEventRecord(g_prof.pending, st);
 }
-void profile_end(cudaStream_t st, double flops) {
+void profile_end(cudaStream_t st, double work) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!g_prof.on || !g_prof.pending) return;
   cudaEvent_t stop = g_prof.get();
   cudaEventRecord(stop, st);
-  g_prof.live.emplace_back(g_prof.pending, stop);
+  g_prof.live.push_back(ProfRecord{g_prof.pending_kernel, g_prof.pending, stop, work});
   g_prof.pending = nullptr;
-  g_prof.flops += flops;
 }
 
 constexpr int kMaxDevices = 64;
@@ -234,23 +239,40 @@ int bo_profile_enable(int on) {
   return BO_OK;
 }
 
-int bo_profile_read(double* total_ms, long long* launches, double* flops) {
+// sums and clears the records of one kernel class (kernel < 0: every class)
+static int profile_collect(int kernel, double* total_ms, long long* launches, double* work) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
-  double ms = 0.0;
-  for (auto& pr : g_prof.live) {
-    BO_CUDA(cudaEventSynchronize(pr.second));
+  double ms = 0.0, wk = 0.0;
+  long long cnt = 0;
+  std::vector<ProfRecord> keep;
+  for (auto& r : g_prof.live) {
+    if (kernel >= 0 && r.kernel != kernel) {
+      keep.push_back(r);
+      continue;
+    }
+    BO_CUDA(cudaEventSynchronize(r.stop));
     float t = 0.f;
-    BO_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+    BO_CUDA(cudaEventElapsedTime(&t, r.start, r.stop));
     ms += t;
-    g_prof.pool.push_back(pr.first);
-    g_prof.pool.push_back(pr.second);
+    wk += r.work;
+    ++cnt;
+    g_prof.pool.push_back(r.start);
+    g_prof.pool.push_back(r.stop);
   }
+  g_prof.live.swap(keep);
   if (total_ms) *total_ms = ms;
-  if (launches) *launches = (long long)g_prof.live.size();
-  if (flops) *flops = g_prof.flops;
-  g_prof.live.clear();
-  g_prof.flops = 0.0;
+  if (launches) *launches = cnt;
+  if (work) *work = wk;
   return BO_OK;
+}
+
+int bo_profile_read(double* total_ms, long long* launches, double* flops) {
+  return profile_collect(BO_PROF_CONTRACTION, total_ms, launches, flops);
+}
+
+int bo_profile_read_kernel(int kernel, double* total_ms, long long* launches, double* work) {
+  BO_REQUIRE(kernel >= -1 && kernel < BO_PROF_KINDS, "unknown kernel class");
+  return profile_collect(kernel, total_ms, launches, work);
 }
 
 int bo_last_clamped_pivots(void) { return g_last_clamped; }
@@ -318,6 +340,8 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
     return BO_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // algorithmic work: Cholesky n^3/3 + triangular inverse n^3/3 + (the W^T W u products are O(n^2)) per objective
+  ProfileScope prof_scope(st, BO_PROF_FIT, (2.0 / 3.0) * m * (double)n * (double)n * (double)n);
   FitBuffers fb;
   carve_fit(&fb, workspace_dev, npad, m);
   const long long strideA = (long long)npad * npad;
@@ -443,6 +467,7 @@ int bo_topk_f64(double* out_val_dev, long long* out_idx_dev, const double* acq_d
                 long long index_base, void* workspace_dev, size_t workspace_bytes, void* stream) {
   BO_REQUIRE(out_val_dev && out_idx_dev && acq_dev && workspace_dev, "null pointer");
   BO_REQUIRE(k >= 1 && k <= BO_MAX_TOPK && n_cand >= 1, "1 <= k <= 1024, n_cand >= 1");
+  ProfileScope prof_scope((cudaStream_t)stream, BO_PROF_TOPK, 8.0 * (double)n_cand);
   return topk_levels(out_val_dev, out_idx_dev, acq_dev, nullptr, n_cand, k, index_base, workspace_dev,
                      workspace_bytes, (cudaStream_t)stream);
 }

@@ -55,8 +55,20 @@ inline int ensure_dynamic_smem(F* fn, size_t bytes) {
 }
 // live CUDA-event timing of the dominant kernel (see bo_profile_enable in bo_b200.h)
 bool profile_enabled();
-void profile_begin(cudaStream_t st);
-void profile_end(cudaStream_t st, double flops);
+void profile_begin(cudaStream_t st, int kernel = BO_PROF_CONTRACTION);  // kernel: a BO_PROF_* class
+void profile_end(cudaStream_t st, double work);  // work: algorithmic flops (contraction) or bytes (the others)
+// brackets one launch (or a short launch sequence) when profiling is on
+struct ProfileScope {
+  cudaStream_t st;
+  double work;
+  bool on;
+  ProfileScope(cudaStream_t s, int kernel, double w) : st(s), work(w), on(profile_enabled()) {
+    if (on) profile_begin(st, kernel);
+  }
+  ~ProfileScope() {
+    if (on) profile_end(st, work);
+  }
+};
 
 // ---------------------------------------------------------------- geometry of the packed operands
 // W (= L^-1, lower triangular, npad x npad) and K* (npad x candidates) are stored as 16 KB tiles in

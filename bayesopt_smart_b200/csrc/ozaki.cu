@@ -856,8 +856,13 @@ int oz_score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind
     const long long remaining = n_cand - cand0;
     const long long live = remaining < p.ld_chunk ? remaining : p.ld_chunk;
     const int tiles = (int)((live + OZ_TN - 1) / OZ_TN);
-    int rc = oz_kstar_digits(kq, meandot, cand, cand_kind, ldc, cand0, n_cand, tiles, p.chunk_tiles, x, ldx, n, d, m,
-                             alpha, hp, stream);
+    int rc;
+    {
+      // algorithmic bytes: six digit planes per K* entry (6 m npad per candidate) + the candidates read
+      ProfileScope prof_scope(stream, BO_PROF_KSTAR, (double)tiles * OZ_TN * ((double)m * p.npad * 6.0 + 8.0 * d));
+      rc = oz_kstar_digits(kq, meandot, cand, cand_kind, ldc, cand0, n_cand, tiles, p.chunk_tiles, x, ldx, n, d, m,
+                           alpha, hp, stream);
+    }
     if (rc) return rc;
     const bool prof = profile_enabled();
     if (prof) profile_begin(stream);

@@ -446,6 +446,11 @@ Overlap* overlap_for_current_device() {
 int finalize_chunk(const ScoreOutputs& out, long long cand0, long long n_cand, const double* part,
                    const double* meandot, long long ld_chunk, int chunk_cands, int nb, int m, const ObjParams& hp,
                    double min_variance, cudaStream_t stream) {
+  const int n_out = (out.mu != nullptr) + (out.var != nullptr) + (out.std_mu != nullptr) + (out.std_var != nullptr) +
+                    (out.ucb != nullptr);
+  // bytes per candidate: (nb + 1) m partials / mean dots read, n_out m + 1 doubles written
+  ProfileScope prof_scope(stream, BO_PROF_FINALIZE,
+                          (double)chunk_cands * 8.0 * ((double)(nb + 1) * m + (double)n_out * m + (out.acq ? 1 : 0)));
   finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb,
                                                                  out.acq, out.ld, cand0, n_cand, part, meandot,
                                                                  ld_chunk, chunk_cands, nb, m, hp, min_variance);
@@ -533,6 +538,8 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     const long long cand0 = ci * p.ld_chunk;
     const int tiles = chunk_tiles_of(ci);
     if (ov && ci >= 2) BO_CUDA(cudaStreamWaitEvent(ov->aux, ov->buffer_free[b], 0));  // TRMM(ci-2) has drained it
+    // algorithmic bytes of this launch: the K* staging it writes (8 m npad per candidate) + the candidates it reads
+    ProfileScope prof_scope(ks_stream, BO_PROF_KSTAR, (double)tiles * TN * ((double)m * p.npad * 8.0 + 8.0 * d));
     int rc;
     if (cand_kind == BO_CAND_I64)
       rc = launch_kstar<long long>(m, d, dim3(2 * tiles), ks_stream, Kp[b], meandot[b],

@@ -252,6 +252,19 @@ long long bo_launch_count(int reset);
  * (m * N^2 per candidate) since the last read, then clears them.                      */
 int bo_profile_enable(int on);
 int bo_profile_read(double* total_ms, long long* launches, double* flops);
+/* The same hook per kernel class: every launch of the scoring pass is bracketed by events while profiling is on.
+ * `work` is the algorithmic work the launches stood for -- FLOPs for BO_PROF_CONTRACTION (m * N^2 per candidate),
+ * bytes for the others (K* staging written, partial sums read + API arrays written, 8 B per scanned score).
+ * kernel = -1 sums (and clears) every class.                                                                */
+enum {
+  BO_PROF_CONTRACTION = 0, /* trmm_sumsq_kernel / oz_sumsq_kernel                               */
+  BO_PROF_KSTAR = 1,       /* kstar_pack_kernel / oz_kstar_digits_kernel                        */
+  BO_PROF_FINALIZE = 2,    /* finalize_kernel (variance, standardise, UCB, acquisition)         */
+  BO_PROF_TOPK = 3,        /* the launches of one bo_topk_f64 call                              */
+  BO_PROF_FIT = 4,         /* the launches of one bo_gp_fit_f64 / bo_gp_append_f64 call         */
+  BO_PROF_KINDS = 5
+};
+int bo_profile_read_kernel(int kernel, double* total_ms, long long* launches, double* work);
 
 #ifdef __cplusplus
 }

@@ -22,10 +22,20 @@ def test_reference_arm_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "candidates/s" and line["dtype"] == "f64"
     assert line["vs_baseline"] is None and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference (oracle/_ref + Numba) when it is available, else the NumPy port with the reason logged
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "bayesopt")):
+        assert line["cpu_baseline"]["kind"] == "reference", line["cpu_baseline"].get("why_port")
+    else:
+        assert "why_port" in line["cpu_baseline"]
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+    # same `config` object as the GPU arm prints (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert line["config"] == bench.headline_config(1)
 
 
 def test_non_zero_ranks_of_reference_arm_exit_quietly():
