@@ -120,6 +120,7 @@ class DeviceGP:
         self.wpack: Optional[torch.Tensor] = None
         self.alpha: Optional[torch.Tensor] = None
         self.prior_mean = self.prior_variance = self.length_scales = None
+        self.clamped_pivots = 0  # Cholesky pivots the last fit clamped to the jitter (0 on well-conditioned input)
 
     # ------------------------------------------------------------------ fit
     def fit(self, x_vector, y_vector, prior_mean, prior_variance, length_scales, current_eval: int,
@@ -142,6 +143,7 @@ class DeviceGP:
         _lib.check(self.lib.bo_gp_fit_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
                                           y.stride(0), n, d, m, pm, pv, pl, float(jitter), _ptr(ws), ws_bytes,
                                           _stream()))
+        self.clamped_pivots = int(self.lib.bo_last_clamped_pivots())
         if self.variance_engine == "int8":
             self.wq = torch.empty(m * self.lib.bo_i8_wq_bytes(n), dtype=torch.uint8, device=self.device)
             self.wscale = torch.empty(self.lib.bo_i8_wscale_doubles(n, m), dtype=_F64, device=self.device)

@@ -120,8 +120,17 @@ def optimize_hyperparams_mll(x_vector, y_vector, kernel_matrix, prior_mean, prio
     returns the SciPy result.  Reference numba_kernels.py:238-321 (Powell settings config.py:73-83).
 
     The training set is uploaded once; each objective evaluation is one batched-MLL call with S = 1.
-    Deviation: ``kernel_matrix`` is not clobbered on every evaluation (the loop rebuilds it right after,
-    bayesian_optimization.py:129).
+    Deviations, both pinned by tests/test_gpu_parity.py::test_powell_fit_matches_reference_trace:
+    * ``kernel_matrix`` is not clobbered on every evaluation (the loop rebuilds it right after,
+      bayesian_optimization.py:129);
+    * the MLL only sees ``K / prior_variance`` (numba_kernels.py:195-197), so the ``prior_variance`` half of the
+      search vector is a flat direction.  The reference evaluates ``pv * exp(.) / pv`` and Powell there walks on
+      rounding noise (3.5426e7 -> 3.5430e7 in BASELINE config 1); the GPU objective works on the correlation matrix
+      directly and is EXACTLY flat in those coordinates.  The fitted variances therefore agree with the
+      reference's only within Powell's ``xtol`` (relative 1e-3), the length scales to ~1e-6.
+    A Gram matrix that is not positive definite raises numpy ``LinAlgError`` like the reference's Cholesky; pivots
+    that rounding merely pushed below the jitter are clamped (count: ``DeviceGP.clamped_pivots`` /
+    ``bo_last_clamped_pivots``).
     """
     dev = require_cuda()
     lib = _lib.load()

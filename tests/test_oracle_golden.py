@@ -162,3 +162,32 @@ def test_workload_generators_match_the_oracle_copies():
         b = wl.make_training_set(name, n, d, seed=3)
         for u, v in zip(a, b):
             assert np.array_equal(u, v)
+
+
+# ------------------------------------------------------------------ BASELINE-scale fixtures (N = 1024, N = 4096)
+def baseline_scale_inputs(g):
+    """Inputs of tests/golden/gp_n{1024,4096}_d6.npz, regenerated from the stored seeds (checksums verified)."""
+    from bayesopt_smart_b200.workloads import make_training_set
+
+    n, d, n_cand = int(g["n"]), int(g["d"]), int(g["n_cand"])
+    x, y, mu0, var0 = make_training_set(str(g["fn"]), n, d, seed=0)
+    cand = np.random.default_rng(int(g["seed_cand"])).random((n_cand, d))
+    cand[5] = x[2]
+    assert x.sum() == float(g["x_checksum"]) and cand.sum() == float(g["cand_checksum"])
+    m = y.shape[1]
+    return n, x, y, cand, mu0, var0, np.full(m, float(g["length_scale"])), np.full(m, float(g["beta"]))
+
+
+@pytest.mark.parametrize("case", ["gp_n1024_d6", "gp_n4096_d6"])
+def test_cholesky_form_matches_reference_at_baseline_scale(golden, case):
+    """The Cholesky form the GPU computes (chol_*) against the reference's explicit-inverse outputs at the cfg2
+    training size (N = 1024, cond 1.3e4) and the north-star size (N = 4096, cond 3.5e6): tolerance
+    max(1e-9, 10 eps cond) in standardised units, identical selected batch."""
+    g = golden(case)
+    n, x, y, cand, mu0, var0, ls, betas = baseline_scale_inputs(g)
+    want = orc.chol_hot_path(x, y, cand, mu0, var0, ls, betas, n, int(g["batch_size"]))
+    tau = max(1e-9, 10 * EPS * float(g["cond"].max()))
+    for o in range(y.shape[1]):
+        assert np.abs(want["mu"][o] - g["mu"][o]).max() / np.sqrt(var0[o]) <= tau
+        assert np.abs(want["var"][o] - g["var"][o]).max() / var0[o] <= tau
+    assert np.array_equal(cand[want["idx"]], g["x_next"])
