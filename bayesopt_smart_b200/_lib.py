@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "bo_b200.h")
 BO_OK, BO_ERR_INVALID, BO_ERR_CUDA, BO_ERR_NOT_PD, BO_ERR_WORKSPACE = 0, 1, 2, 3, 4
 BO_CAND_F64, BO_CAND_I64 = 0, 1
 BO_MAX_OBJECTIVES, BO_MAX_DIMS, BO_MAX_TOPK, BO_TILE = 4, 16, 1024, 128
+BO_MAX_APPEND = 32
 BO_PROF_CONTRACTION, BO_PROF_KSTAR, BO_PROF_FINALIZE, BO_PROF_TOPK, BO_PROF_FIT = 0, 1, 2, 3, 4
 
 
@@ -41,6 +42,8 @@ _SIGNATURES = {
     "bo_fit_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bo_gp_fit_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _dp, _dp,
                               _dp, c_double, c_void_p, c_size_t, c_void_p]),
+    "bo_gp_append_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 _dp, _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
     "bo_score_workspace_bytes": (c_size_t, [c_int, c_int, c_longlong]),
     "bo_score_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                              c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, _dp, _dp,

@@ -25,6 +25,8 @@ from .pareto import compute_pareto_front, is_pareto_efficient, print_pareto_anal
 _HOST_BUFFERS = {"mu": "mu_objectives", "var": "variance_objectives", "std_mu": "std_mu_objectives",
                  "std_var": "std_variance_objectives", "ucb": "ucb", "acq": "acquisition_values"}
 _TIMING_KEYS = ("hyperparams", "kernels", "acquisition", "eval", "total")
+# diagnostics of the most recent optimize() call in this process: how each iteration obtained its factor
+LAST_RUN_INFO = {"fit_modes": [], "clamped_pivots": []}
 
 
 class _Clock:
@@ -68,7 +70,7 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
              std_variance_objectives, ucb, acquisition_values, input_space, prior_mean, prior_variance,
              reference_point, n_evaluations, total_samples, n_objectives, function, betas, length_scales,
              batch_size, bounds, callbacks=None, acquisition="sum_ucb", variance_engine=None,
-             candidates_from_bounds=False):
+             candidates_from_bounds=False, hyperparam_tolerance=0.0):
     """The BO loop; same parameters and return value as the reference (:51-247).
 
     Each iteration: Powell fit of (length_scales, prior_variance) on the GPU log marginal likelihood,
@@ -79,6 +81,13 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
     untouched (K* is never materialised).  ``acquisition="exact_hvi"`` swaps the reference's sum-UCB score
     for the exact hypervolume improvement (2 or 3 objectives).  Returns ``(x_vector, y_vector,
     last_eval + 1)`` -- the reference's own off-by-batch quirk (:247).
+
+    Factor reuse: the training rows, the Cholesky factor and ``W = L^-1`` stay resident in HBM
+    between iterations.  If the Powell fit of an iteration leaves every length scale and prior variance within
+    the RELATIVE ``hyperparam_tolerance`` of the values the resident factor was built with, those values are kept
+    (written back into ``length_scales`` / ``prior_variance``) and the factor is extended by the ``batch_size``
+    new rows in O(batch N^2) instead of being rebuilt in O(N^3).  The default 0.0 reuses the factor only when
+    Powell returns bit-identical hyper-parameters, i.e. the loop then computes exactly what the reference does.
 
     Multi-GPU: when ``torch.distributed`` is initialised (one process per GPU) every rank calls this with
     the same arguments; rank r scores candidates ``distributed.shard_range(M, world, r)``, the per-rank
@@ -103,16 +112,26 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
     staging = PinnedMirror()
     starts = range(n_evaluations, total_samples, batch_size)
     last_eval = 0
+    LAST_RUN_INFO["fit_modes"], LAST_RUN_INFO["clamped_pivots"] = [], []
 
     for current_eval in starts:
         clock = _Clock()
         fitted = optimize_hyperparams_mll(x_vector=x_vector, y_vector=y_vector, kernel_matrix=kernel_matrices,
                                           prior_mean=prior_mean, prior_variance=prior_variance,
                                           length_scales=length_scales, current_eval=current_eval)
+        if gp.length_scales is not None and hyperparam_tolerance > 0.0:
+            m_obj = y_vector.shape[1]
+            old = np.concatenate([gp.length_scales[:m_obj], gp.prior_variance[:m_obj]])
+            new = np.concatenate([length_scales, prior_variance])
+            if np.all(np.abs(new - old) <= hyperparam_tolerance * np.abs(old)):
+                length_scales[:] = old[:m_obj]      # keep the resident factor's hyper-parameters: it is extended,
+                prior_variance[:] = old[m_obj:]     # not rebuilt (fitted.x still reports what Powell returned)
         clock.tick()
 
         seen_x, seen_y = x_vector[:current_eval], y_vector[:current_eval]
         gp.fit(seen_x, seen_y, prior_mean, prior_variance, length_scales, current_eval)
+        LAST_RUN_INFO["fit_modes"].append(gp.last_fit)
+        LAST_RUN_INFO["clamped_pivots"].append(gp.clamped_pivots)
         torch.cuda.synchronize()
         clock.tick()
 
@@ -180,6 +199,7 @@ class BayesianOptimization:
         self.initial_samples = kwargs.get("initial_samples", cfg.DEFAULT_INITIAL_SAMPLES)
         self.acquisition = kwargs.get("acquisition", "sum_ucb")
         self.variance_engine = kwargs.get("variance_engine")  # None: "dmma" (or BO_VARIANCE_ENGINE); "int8"
+        self.hyperparam_tolerance = float(kwargs.get("hyperparam_tolerance", 0.0))  # > 0: reuse + extend the factor
 
         # candidate set: every integer point of the box, upper bounds exclusive (:338-340)
         axes = np.meshgrid(*[np.arange(lo, hi) for lo, hi in bounds], indexing="ij")
@@ -233,7 +253,7 @@ class BayesianOptimization:
                     "n_objectives", "function", "betas", "length_scales", "batch_size", "bounds")}
         self.x_vector, self.y_vector, self.n_evaluations = optimize(
             **buffers, callbacks=self.callbacks or None, acquisition=self.acquisition,
-            variance_engine=self.variance_engine,
+            variance_engine=self.variance_engine, hyperparam_tolerance=self.hyperparam_tolerance,
             candidates_from_bounds=self._input_space_is_the_integer_grid())
 
     def pareto_analysis(self) -> np.ndarray:

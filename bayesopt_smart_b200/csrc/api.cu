@@ -157,7 +157,7 @@ __global__ void grid_kernel(long long* __restrict__ out, long long ld, GridSpec 
 }
 
 struct FitBuffers {
-  double *A, *W, *T, *D, *scratch, *pol;
+  double *A, *W, *T, *D, *scratch, *pol, *append;
   int* info;
 };
 
@@ -181,6 +181,8 @@ size_t carve_fit(FitBuffers* fb, void* ws, int npad, int m) {
   off += align256((size_t)2 * m * sizeof(int));
   if (fb) fb->pol = reinterpret_cast<double*>(p + off);
   off += align256((size_t)2 * m * sizeof(double));
+  if (fb) fb->append = reinterpret_cast<double*>(p + off);
+  off += align256(append_scratch_doubles(npad, m) * sizeof(double));
   return off;
 }
 
@@ -354,6 +356,51 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
   rc = pack_w(wpack_dev, (long long)bo_wpack_doubles(n), fb.W, npad, strideA, npad, n, m, st);
   if (rc) return rc;
   BO_CUDA(cudaStreamSynchronize(st));
+  return BO_OK;
+}
+
+int bo_gp_append_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int ldx, const double* y_dev, int ldy,
+                     int n_old, int n_new, int d, int m, const double* prior_mean_host,
+                     const double* prior_variance_host, const double* length_scales_host, double jitter,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(wpack_dev && alpha_dev && x_dev && y_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host, "null hyper-parameter pointer");
+  BO_REQUIRE(n_old >= 1 && n_new > n_old && n_new - n_old <= BO_MAX_APPEND && d >= 1 && d <= BO_MAX_DIMS,
+             "bad sizes (1 <= n_new - n_old <= BO_MAX_APPEND)");
+  BO_REQUIRE(round_up(n_new, TM) == round_up(n_old, TM),
+             "n_new leaves the 128-row padding of the existing factor: refit with bo_gp_fit_f64");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  const int npad = round_up(n_new, TM);
+  if (workspace_bytes < bo_fit_workspace_bytes(n_new, m)) {
+    set_error("fit workspace too small: %zu < %zu", workspace_bytes, bo_fit_workspace_bytes(n_new, m));
+    return BO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // algorithmic work: two triangular products with the b new columns per objective
+  ProfileScope prof_scope(st, BO_PROF_FIT, 2.0 * m * (double)(n_new - n_old) * (double)n_old * (double)n_old);
+  FitBuffers fb;
+  carve_fit(&fb, workspace_dev, npad, m);
+  const long long strideA = (long long)npad * npad;
+  BO_CUDA(cudaMemsetAsync(fb.info, 0, sizeof(int) * 2 * m, st));
+  rc = append_rows(fb.A, fb.W, npad, strideA, x_dev, ldx, n_old, n_new, npad, d, m, hp, jitter, fb.append, fb.info, st);
+  if (rc) return rc;
+  rc = compute_alpha(alpha_dev, fb.W, npad, strideA, y_dev, ldy, n_new, npad, m, hp, fb.scratch, st);
+  if (rc) return rc;
+  rc = pack_w(wpack_dev, (long long)bo_wpack_doubles(n_new), fb.W, npad, strideA, npad, n_new, m, st);
+  if (rc) return rc;
+  int info_h[2 * BO_MAX_OBJECTIVES] = {0, 0, 0, 0, 0, 0, 0, 0};
+  BO_CUDA(cudaMemcpyAsync(info_h, fb.info, sizeof(int) * 2 * m, cudaMemcpyDeviceToHost, st));
+  BO_CUDA(cudaStreamSynchronize(st));
+  g_last_clamped = 0;
+  for (int o = 0; o < m; ++o) g_last_clamped += info_h[m + o];
+  for (int o = 0; o < m; ++o) {
+    if (info_h[o] != 0) {
+      set_error("Matrix is not positive definite (objective %d, pivot %d of the appended rows)", o, info_h[o]);
+      return BO_ERR_NOT_PD;
+    }
+  }
   return BO_OK;
 }
 

@@ -357,9 +357,202 @@ __global__ void __launch_bounds__(256) pack_w_kernel(double* __restrict__ Wp, lo
   (void)nb;
 }
 
+// ----------------------------------------------------------------------------------------- incremental append
+// (f)2 of SURVEY 8: the reference rebuilds K and its inverse from scratch every iteration
+// (bayesian_optimization.py:129-142, last_eval = 0).  When the hyper-parameters did not change, the factor of the
+// first n_old points is still valid and the b = n_new - n_old new points only add b rows:
+//   K_new = [K11 K12; K21 K22],  L21 = (W11 K12)^T,  L22 L22^T = K22 + jitter I - L21 L21^T,
+//   W_new = [W11 0; W21 W22],    W22 = L22^-1,       W21 = -W22 (L21 W11)
+// O(b N^2) instead of O(N^3).  The new rows replace identity-padding rows of the padded work matrices, so the
+// update is in place as long as n_new stays inside the same 128-row padding (otherwise the caller refits).
+
+// Kc[o][j][i] = K_o(x_i, x_{n_old+j}) (+ jitter on the diagonal entry i = n_old + j), i < n_new
+__global__ void __launch_bounds__(256)
+    append_cross_kernel(double* __restrict__ Kc, int ldkc, const double* __restrict__ x, int ldx, int n_old, int n_new,
+                        int d, ObjParams hp, double jitter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, o = blockIdx.z, b = n_new - n_old;
+  if (i >= n_new) return;
+  double sq = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double diff = x[(long long)i * ldx + k] - x[(long long)(n_old + j) * ldx + k];
+    sq = fma(diff, diff, sq);
+  }
+  double v = hp.prior_var[o] * rbf_exp(sq * hp.neg_half_inv_ls2[o], kExp2Tab);
+  if (i == n_old + j) v += jitter;
+  Kc[((long long)o * b + j) * ldkc + i] = v;
+}
+
+// S[o][j][i] = sum_{k<=i} W[i][k] Kc[o][j][k]   (= L21[j][i]), one warp per row i < n_old, all b columns
+__global__ void __launch_bounds__(256)
+    append_forward_kernel(double* __restrict__ S, const double* __restrict__ Kc, int ldkc, const double* __restrict__ W,
+                          long long ldw, long long strideW, int n_old, int b) {
+  const int o = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_old) return;
+  const double* Wr = W + o * strideW + (long long)row * ldw;
+  for (int j = 0; j < b; ++j) {
+    const double* kc = Kc + ((long long)o * b + j) * ldkc;
+    double s = 0.0;
+    for (int k = lane; k <= row; k += 32) s = fma(Wr[k], kc[k], s);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) S[((long long)o * b + j) * ldkc + row] = s;
+  }
+}
+
+// One CTA per objective: Schur complement C = K22 + jitter I - L21 L21^T (b x b), its Cholesky factor L22 (same
+// pivot policy as potf2_kernel) and W22 = L22^-1.  small[o] = [L22 (b*b) | W22 (b*b)], row-major.
+__global__ void __launch_bounds__(256)
+    append_schur_kernel(double* __restrict__ small, int* __restrict__ info, const double* __restrict__ S,
+                        const double* __restrict__ Kc, int ldkc, int n_old, int b, int m, double jitter) {
+  __shared__ double C[BO_MAX_APPEND][BO_MAX_APPEND + 1];
+  __shared__ double X[BO_MAX_APPEND][BO_MAX_APPEND + 1];
+  const int o = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* So = S + (long long)o * b * ldkc;
+  const double* Ko = Kc + (long long)o * b * ldkc;
+  for (int p = warp; p < b * b; p += 8) {
+    const int j = p / b, l = p % b;
+    if (l > j) continue;
+    double s = 0.0;
+    for (int i = lane; i < n_old; i += 32) s = fma(So[(long long)j * ldkc + i], So[(long long)l * ldkc + i], s);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) C[j][l] = Ko[(long long)j * ldkc + n_old + l] - s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = 0.0;
+    for (int j = 0; j < b; ++j) mx = fmax(mx, fabs(Ko[(long long)j * ldkc + n_old + j]));
+    const double floor_piv = fmax(jitter, 2.220446049250313e-16 * mx), neg_tol = 1.4901161193847656e-08 * mx;
+    int bad = 0, nclamp = 0;
+    for (int j = 0; j < b; ++j) {
+      double piv = C[j][j];
+      for (int k = 0; k < j; ++k) piv = fma(-C[j][k], C[j][k], piv);
+      if (!(piv >= floor_piv)) {
+        if (piv > -neg_tol) ++nclamp;
+        else if (bad == 0) bad = n_old + j + 1;
+        piv = floor_piv;
+      }
+      const double ljj = sqrt(piv);
+      C[j][j] = ljj;
+      for (int i = j + 1; i < b; ++i) {
+        double v = C[i][j];
+        for (int k = 0; k < j; ++k) v = fma(-C[i][k], C[j][k], v);
+        C[i][j] = v / ljj;
+      }
+    }
+    // W22 = L22^-1 by forward substitution, column by column
+    for (int c = 0; c < b; ++c) {
+      for (int i = 0; i < b; ++i) {
+        if (i < c) { X[i][c] = 0.0; continue; }
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) v = fma(-C[i][k], X[k][c], v);
+        X[i][c] = v / C[i][i];
+      }
+    }
+    info[o] = bad;
+    info[m + o] = nclamp;
+  }
+  __syncthreads();
+  double* out = small + (long long)o * 2 * b * b;
+  for (int p = threadIdx.x; p < b * b; p += blockDim.x) {
+    const int j = p / b, l = p % b;
+    out[p] = (l <= j) ? C[j][l] : 0.0;
+    out[b * b + p] = X[j][l];
+  }
+}
+
+// part[o][rs][j][c] = sum over rows i of split rs (i >= c) of S[o][j][i] W[i][c]      (T = L21 W11, thread per column)
+constexpr int APPEND_SPLIT = 8;
+__global__ void __launch_bounds__(128)
+    append_backward_partial_kernel(double* __restrict__ part, const double* __restrict__ S, int ldkc,
+                                   const double* __restrict__ W, long long ldw, long long strideW, int n_old, int b,
+                                   int rows_per) {
+  const int o = blockIdx.z, rs = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i_lo = rs * rows_per, i_hi = min((rs + 1) * rows_per, n_old);
+  const double* Wo = W + o * strideW;
+  const double* So = S + (long long)o * b * ldkc;
+  for (int j0 = 0; j0 < b; j0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    if (c < n_old) {
+      for (int i = max(i_lo, c); i < i_hi; ++i) {
+        const double w = Wo[(long long)i * ldw + c];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (j0 + q < b) acc[q] = fma(So[(long long)(j0 + q) * ldkc + i], w, acc[q]);  // warp-uniform address
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (j0 + q < b) part[(((long long)o * APPEND_SPLIT + rs) * b + j0 + q) * ldkc + c] = acc[q];
+    }
+  }
+}
+
+// rows n_old + j of L and W:  L = [S | L22 | 0],  W = [-W22 T | W22 | 0]   (T = sum of the partials, fixed order)
+__global__ void __launch_bounds__(256)
+    append_write_rows_kernel(double* __restrict__ L, double* __restrict__ W, long long ld, long long stride,
+                             const double* __restrict__ S, const double* __restrict__ part,
+                             const double* __restrict__ small, int ldkc, int n_old, int b, int npad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, o = blockIdx.z;
+  if (c >= npad) return;
+  const double* L22 = small + (long long)o * 2 * b * b;
+  const double* W22 = L22 + b * b;
+  double lv = 0.0, wv = 0.0;
+  if (c < n_old) {
+    lv = S[((long long)o * b + j) * ldkc + c];
+    double t = 0.0;
+    for (int l = 0; l <= j; ++l) {  // W22 is lower triangular
+      double tl = 0.0;
+      for (int rs = 0; rs < APPEND_SPLIT; ++rs) tl += part[(((long long)o * APPEND_SPLIT + rs) * b + l) * ldkc + c];
+      t = fma(W22[j * b + l], tl, t);
+    }
+    wv = -t;
+  } else if (c < n_old + b) {
+    const int l = c - n_old;
+    lv = (l <= j) ? L22[j * b + l] : 0.0;
+    wv = (l <= j) ? W22[j * b + l] : 0.0;
+  }
+  L[o * stride + (long long)(n_old + j) * ld + c] = lv;
+  W[o * stride + (long long)(n_old + j) * ld + c] = wv;
+}
+
 }  // namespace
 
 // =========================================================================================== host drivers
+size_t append_scratch_doubles(int npad, int m) {
+  // Kc + S: 2 * b * npad; partials: APPEND_SPLIT * b * npad; small: 2 b^2   (b <= BO_MAX_APPEND), per objective
+  return (size_t)m * ((size_t)(2 + APPEND_SPLIT) * BO_MAX_APPEND * npad + 2 * BO_MAX_APPEND * BO_MAX_APPEND);
+}
+
+int append_rows(double* L, double* W, long long ld, long long stride, const double* x, int ldx, int n_old, int n_new,
+                int npad, int d, int m, const ObjParams& hp, double jitter, double* scratch, int* info,
+                cudaStream_t stream) {
+  const int b = n_new - n_old;
+  double* Kc = scratch;
+  double* S = Kc + (size_t)m * b * npad;
+  double* part = S + (size_t)m * b * npad;
+  double* small = part + (size_t)m * APPEND_SPLIT * b * npad;
+  append_cross_kernel<<<dim3((n_new + 255) / 256, b, m), 256, 0, stream>>>(Kc, npad, x, ldx, n_old, n_new, d, hp, jitter);
+  BO_LAUNCH_CHECK("append_cross_kernel");
+  append_forward_kernel<<<dim3((n_old + 7) / 8, m), 256, 0, stream>>>(S, Kc, npad, W, ld, stride, n_old, b);
+  BO_LAUNCH_CHECK("append_forward_kernel");
+  append_schur_kernel<<<m, 256, 0, stream>>>(small, info, S, Kc, npad, n_old, b, m, jitter);
+  BO_LAUNCH_CHECK("append_schur_kernel");
+  const int rows_per = (n_old + APPEND_SPLIT - 1) / APPEND_SPLIT;
+  append_backward_partial_kernel<<<dim3((n_old + 127) / 128, APPEND_SPLIT, m), 128, 0, stream>>>(part, S, npad, W, ld,
+                                                                                                stride, n_old, b, rows_per);
+  BO_LAUNCH_CHECK("append_backward_partial_kernel");
+  append_write_rows_kernel<<<dim3((npad + 255) / 256, b, m), 256, 0, stream>>>(L, W, ld, stride, S, part, small, npad,
+                                                                              n_old, b, npad);
+  BO_LAUNCH_CHECK("append_write_rows_kernel");
+  return BO_OK;
+}
+
 int gram(double* K, long long ldk, long long strideK, const double* x, int ldx, int last_eval, int n, int npad_rows,
          int d, int m, const ObjParams& hp, double diag_add, cudaStream_t stream, bool lower_only) {
   const int span = npad_rows - last_eval;

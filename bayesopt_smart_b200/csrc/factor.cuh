@@ -27,6 +27,14 @@ int compute_alpha(double* alpha, const double* W, long long ldw, long long strid
                   int npad, int m, const ObjParams& hp, double* scratch, cudaStream_t stream);
 size_t alpha_scratch_doubles(int npad, int m);
 
+// Incremental update: rows [n_old, n_new) of the padded dense L and W = L^-1 (both npad x npad, the
+// state bo_gp_fit_f64 leaves in its workspace) are computed from the existing factor of the first n_old points.
+// b = n_new - n_old <= BO_MAX_APPEND, and n_new <= npad.  info: 2*m ints (failed pivot, clamped pivots).
+size_t append_scratch_doubles(int npad, int m);
+int append_rows(double* L, double* W, long long ld, long long stride, const double* x, int ldx, int n_old, int n_new,
+                int npad, int d, int m, const ObjParams& hp, double jitter, double* scratch, int* info,
+                cudaStream_t stream);
+
 // W -> fragment-ordered 16 KB tiles (see common.cuh)
 int pack_w(double* Wp, long long strideWp, const double* W, long long ldw, long long strideW, int npad, int n, int m,
            cudaStream_t stream);

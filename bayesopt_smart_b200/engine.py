@@ -121,38 +121,114 @@ class DeviceGP:
         self.alpha: Optional[torch.Tensor] = None
         self.prior_mean = self.prior_variance = self.length_scales = None
         self.clamped_pivots = 0  # Cholesky pivots the last fit clamped to the jitter (0 on well-conditioned input)
+        self.last_fit = None     # "full" or "append": how the last fit() produced the factor
+        self.y: Optional[torch.Tensor] = None
+        self._fit_key = None     # (prior_mean, prior_variance, length_scales, jitter) of the resident factor
 
     # ------------------------------------------------------------------ fit
-    def fit(self, x_vector, y_vector, prior_mean, prior_variance, length_scales, current_eval: int,
-            jitter: float = KERNEL_JITTER) -> None:
-        """Factor K + jitter I for the first ``current_eval`` rows.  Raises numpy LinAlgError if not PD."""
-        n = int(current_eval)
-        x = to_device(x_vector, _F64, self.device)
-        y = to_device(y_vector, _F64, self.device)
-        if x.dim() != 2 or y.dim() != 2 or x.shape[0] < n or y.shape[0] < n:
+    def _stage_training(self, x_vector, y_vector, n: int, compare: bool = True):
+        """Training rows -> device tensors (n, d), (n, m), plus whether the rows of the resident factor are an
+        unchanged prefix of them.  Host (NumPy) inputs are compared with the host copy kept from the last fit and
+        only the NEW rows are uploaded into the resident buffers; device tensors are compared on the device."""
+        n_old = self.n if self.wpack is not None else 0
+        if isinstance(x_vector, torch.Tensor) or isinstance(y_vector, torch.Tensor):
+            x = to_device(x_vector, _F64, self.device)
+            y = to_device(y_vector, _F64, self.device)
+            if x.dim() != 2 or y.dim() != 2 or x.shape[0] < n or y.shape[0] < n:
+                raise ValueError("x_vector (T,d) and y_vector (T,m) must hold at least current_eval rows")
+            same = bool(compare and 0 < n_old <= n and self.x is not None and x.shape[1] == self.x.shape[1]
+                        and y.shape[1] == self.y.shape[1] and torch.equal(x[:n_old], self.x[:n_old])
+                        and torch.equal(y[:n_old], self.y[:n_old]))
+            self._x_host = self._y_host = None
+            return x[:n].clone(), y[:n].clone(), same
+        xh = np.ascontiguousarray(np.asarray(x_vector, dtype=np.float64))
+        yh = np.ascontiguousarray(np.asarray(y_vector, dtype=np.float64))
+        if xh.ndim != 2 or yh.ndim != 2 or xh.shape[0] < n or yh.shape[0] < n:
             raise ValueError("x_vector (T,d) and y_vector (T,m) must hold at least current_eval rows")
-        d, m = x.shape[1], y.shape[1]
-        npad = self.lib.bo_npad(n)
-        self.wpack = torch.empty(m * self.lib.bo_wpack_doubles(n), dtype=_F64, device=self.device)
-        self.alpha = torch.empty(m * npad, dtype=_F64, device=self.device)
-        ws_bytes = self.lib.bo_fit_workspace_bytes(n, m)
-        ws = self.ws.get("fit", ws_bytes, self.device)
+        xh, yh = xh[:n], yh[:n]
+        hx, hy = getattr(self, "_x_host", None), getattr(self, "_y_host", None)
+        same = bool(0 < n_old <= n and hx is not None and hx.shape[1] == xh.shape[1] and hy.shape[1] == yh.shape[1]
+                    and np.array_equal(xh[:n_old], hx[:n_old]) and np.array_equal(yh[:n_old], hy[:n_old]))
+        res_x, res_y = getattr(self, "_x_res", None), getattr(self, "_y_res", None)
+        if same and res_x is not None and res_x.shape[0] >= n:
+            if n > n_old:  # only the new rows cross PCIe; the prefix is already resident
+                res_x[n_old:n].copy_(torch.from_numpy(xh[n_old:n]))
+                res_y[n_old:n].copy_(torch.from_numpy(yh[n_old:n]))
+        else:
+            cap = self.lib.bo_npad(n) + _lib.BO_TILE
+            res_x = torch.empty((cap, xh.shape[1]), dtype=_F64, device=self.device)
+            res_y = torch.empty((cap, yh.shape[1]), dtype=_F64, device=self.device)
+            res_x[:n].copy_(torch.from_numpy(xh))
+            res_y[:n].copy_(torch.from_numpy(yh))
+            self._x_res, self._y_res = res_x, res_y
+        self._x_host, self._y_host = xh.copy(), yh.copy()
+        return res_x[:n], res_y[:n], same
+
+    def _can_append(self, n: int, d: int, m: int, hyper_key) -> bool:
+        """The resident factor can be extended by the rows [self.n, n): same hyper-parameters bit
+        for bit, same 128-row padding, at most BO_MAX_APPEND new rows, and no clamped pivots in the factor."""
+        if self.wpack is None or self._fit_key is None:
+            return False
+        n_old = self.n
+        if not (0 < n_old < n <= n_old + _lib.BO_MAX_APPEND) or self.lib.bo_npad(n) != self.lib.bo_npad(n_old):
+            return False
+        if self.clamped_pivots or d != self.d or m != self.m:
+            return False  # a factor that needed pivot clamping (cond ~ 1e15) is not extended, it is rebuilt
+        return hyper_key == self._fit_key
+
+    def fit(self, x_vector, y_vector, prior_mean, prior_variance, length_scales, current_eval: int,
+            jitter: float = KERNEL_JITTER, incremental: bool = True) -> None:
+        """Factor K + jitter I for the first ``current_eval`` rows.  Raises numpy LinAlgError if not PD.
+
+        The training rows, the dense factor and ``W = L^-1`` stay resident in HBM between calls.  ``incremental``
+        (default on): when the previous fit of this object used bit-identical hyper-parameters and its training
+        rows are an unchanged prefix of the new ones, the factor is EXTENDED by the new rows
+        (``bo_gp_append_f64``, O(b n^2)) instead of rebuilt (O(n^3)); ``self.last_fit`` says which happened
+        ("full" or "append").  The reference always rebuilds (bayesian_optimization.py:129-142); the extended
+        factor equals the rebuilt one up to rounding (tests/test_gpu_append.py).
+        """
+        n = int(current_eval)
+        d, m = int(np.shape(x_vector)[1]), int(np.shape(y_vector)[1])
         self._mean_h, pm = _lib.host_doubles(prior_mean, m)
         self._var_h, pv = _lib.host_doubles(prior_variance, m)
         self._ls_h, pl = _lib.host_doubles(length_scales, m)
-        _lib.check(self.lib.bo_gp_fit_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
-                                          y.stride(0), n, d, m, pm, pv, pl, float(jitter), _ptr(ws), ws_bytes,
-                                          _stream()))
+        hyper_key = (tuple(self._mean_h[:m].tolist()), tuple(self._var_h[:m].tolist()), tuple(self._ls_h[:m].tolist()),
+                     float(jitter))
+        may_append = bool(incremental and self._can_append(n, d, m, hyper_key))
+        # the prefix comparison of device tensors costs a host synchronisation: only done when an append is possible
+        x, y, prefix_same = self._stage_training(x_vector, y_vector, n, compare=may_append)
+        npad = self.lib.bo_npad(n)
+        ws_bytes = self.lib.bo_fit_workspace_bytes(n, m)
+        appended = False
+        if may_append and prefix_same:
+            ws = self.ws.get("fit", ws_bytes, self.device)  # same size as at the last fit: the buffer (L, W) is reused
+            try:
+                _lib.check(self.lib.bo_gp_append_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
+                                                     y.stride(0), self.n, n, d, m, pm, pv, pl, float(jitter), _ptr(ws),
+                                                     ws_bytes, _stream()))
+                appended = True
+            except np.linalg.LinAlgError:
+                appended = False  # the Schur complement lost definiteness in rounding: rebuild from scratch
+        if not appended:
+            self.wpack = torch.empty(m * self.lib.bo_wpack_doubles(n), dtype=_F64, device=self.device)
+            self.alpha = torch.empty(m * npad, dtype=_F64, device=self.device)
+            ws = self.ws.get("fit", ws_bytes, self.device)
+            _lib.check(self.lib.bo_gp_fit_f64(_ptr(self.wpack), _ptr(self.alpha), _ptr(x), x.stride(0), _ptr(y),
+                                              y.stride(0), n, d, m, pm, pv, pl, float(jitter), _ptr(ws), ws_bytes,
+                                              _stream()))
+        self.last_fit = "append" if appended else "full"
         self.clamped_pivots = int(self.lib.bo_last_clamped_pivots())
         if self.variance_engine == "int8":
             self.wq = torch.empty(m * self.lib.bo_i8_wq_bytes(n), dtype=torch.uint8, device=self.device)
             self.wscale = torch.empty(self.lib.bo_i8_wscale_doubles(n, m), dtype=_F64, device=self.device)
             _lib.check(self.lib.bo_i8_quantize_w(_ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack), n, m,
                                                  _stream()))
-        self.x, self.n, self.d, self.m = x, n, d, m
+        self.x, self.y = x, y
+        self.n, self.d, self.m = n, d, m
         self.prior_mean = self._mean_h.copy()
         self.prior_variance = self._var_h.copy()
         self.length_scales = self._ls_h.copy()
+        self._fit_key = hyper_key
 
     # ------------------------------------------------------------------ score
     def score(self, candidates, betas, *, want=("mu", "var", "acq"), out: Optional[Dict[str, torch.Tensor]] = None,

@@ -25,6 +25,7 @@ CPU oracle; the oracle is used as the checker only):
     cfg3        ZDT2 d=10, N=4096, m=2, 16 M candidates                 (N >= 2; both engines)
     cfg5        256-setting log-marginal-likelihood sweep at N=4096     (settings sharded over the ranks)
     hbm_passes  stand-alone score pass / top-k scan at 16 M candidates  (rank 0)
+    incremental_fit  factor extended by a batch of 3 points vs rebuilt, N = 1024 / 4096 (rank 0)
     cfg1_loop   the reference's demo through BayesianOptimization(...).optimize(), Powell fit included (rank 0)
 
 `cpu_baseline` / `--impl reference`: the UNMODIFIED reference functions (oracle/_ref, a git-ignored verbatim
@@ -599,6 +600,43 @@ def run_hbm_passes(dev, peaks, lib):
     return out
 
 
+def run_incremental_fit(dev):
+    """time saved per iteration when the resident factor is extended by a batch of 3 new points
+    (bo_gp_append_f64) instead of rebuilt (bo_gp_fit_f64) -- rank 0, CUDA events, best of 3."""
+    import torch
+
+    from bayesopt_smart_b200.engine import DeviceGP
+    from bayesopt_smart_b200.workloads import make_training_set
+
+    out = {}
+    for n in (1024, 4096):
+        x, y, mu0, var0 = make_training_set("zdt1", n, 6, seed=0)
+        ls = np.full(2, 0.3)
+        gp = DeviceGP(dev)
+        full, app = [], []
+        for _ in range(4):
+            gp.fit(x, y, mu0, var0, ls, n - 3, incremental=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gp.fit(x, y, mu0, var0, ls, n)
+            e1.record()
+            torch.cuda.synchronize()
+            assert gp.last_fit == "append"
+            app.append(e0.elapsed_time(e1))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gp.fit(x, y, mu0, var0, ls, n, incremental=False)
+            e1.record()
+            torch.cuda.synchronize()
+            full.append(e0.elapsed_time(e1))
+        out[f"n{n}"] = {"full_refit_ms": min(full[1:]), "append_3_rows_ms": min(app[1:]),
+                        "speedup": min(full[1:]) / min(app[1:])}
+    out["what"] = "DeviceGP.fit with an unchanged prefix and bit-identical hyper-parameters extends L, W = L^-1 " \
+                  "and alpha by the new rows (O(b N^2)); the reference rebuilds everything (O(N^3))"
+    return out
+
+
 def run_cfg1_loop():
     """BASELINE configs[0] through the drop-in class, Powell hyper-parameter fit included (a
     full-iteration number next to the hot-path figure)."""
@@ -806,7 +844,8 @@ def run_gpu_arm(args):
         except Exception as exc:  # noqa: BLE001
             extras["cfg5"] = {"error": f"{type(exc).__name__}: {exc}"}
         if rank == 0:
-            for label, fn in (("hbm_passes", lambda: run_hbm_passes(dev, peaks, lib)), ("cfg1_loop", run_cfg1_loop)):
+            for label, fn in (("hbm_passes", lambda: run_hbm_passes(dev, peaks, lib)),
+                              ("incremental_fit", lambda: run_incremental_fit(dev)), ("cfg1_loop", run_cfg1_loop)):
                 if world > 1 and label == "cfg1_loop":
                     continue  # BayesianOptimization.optimize() would shard over the process group
                 try:

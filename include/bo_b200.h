@@ -52,6 +52,7 @@ enum { BO_CAND_F64 = 0, BO_CAND_I64 = 1 };
 #define BO_MAX_DIMS 16      /* d: input dimensions                               */
 #define BO_MAX_TOPK 1024    /* k of bo_topk_f64                                  */
 #define BO_TILE 128         /* training rows are padded to a multiple of this    */
+#define BO_MAX_APPEND 32    /* rows bo_gp_append_f64 adds in one call            */
 
 int bo_abi_version(void);
 const char* bo_last_error(void);
@@ -92,6 +93,22 @@ int bo_gp_fit_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int
                   int n, int d, int m, const double* prior_mean_host, const double* prior_variance_host,
                   const double* length_scales_host, double jitter, void* workspace_dev, size_t workspace_bytes,
                   void* stream);
+
+/* ------------------------------------------- incremental factor update
+ * The reference rebuilds K and its inverse from scratch every iteration (update_k / invert_k are called with
+ * last_eval = 0, bayesian_optimization.py:129-142).  When the hyper-parameters are unchanged the factor of the
+ * first n_old points stays valid; this call adds the rows of points [n_old, n_new):
+ *   L21 = (W11 K12)^T,  L22 L22^T = K22 + jitter I - L21 L21^T,  W22 = L22^-1,  W21 = -W22 L21 W11,
+ * then recomputes alpha and re-packs W: O((n_new - n_old) n^2) instead of O(n^3).
+ * `workspace_dev` MUST be the workspace of the preceding bo_gp_fit_f64 / bo_gp_append_f64 call for the same
+ * training prefix, untouched since (it holds the dense L and W); x_dev / y_dev hold all n_new rows; the
+ * hyper-parameters and jitter must be the ones of that fit.  Requirements: n_new - n_old <= BO_MAX_APPEND and
+ * bo_npad(n_new) == bo_npad(n_old) (otherwise BO_ERR_INVALID: refit).  Same pivot policy and error codes as
+ * bo_gp_fit_f64.  Synchronising.                                                                      */
+int bo_gp_append_f64(double* wpack_dev, double* alpha_dev, const double* x_dev, int ldx, const double* y_dev, int ldy,
+                     int n_old, int n_new, int d, int m, const double* prior_mean_host,
+                     const double* prior_variance_host, const double* length_scales_host, double jitter,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------- a3..a8 fused: predict + UCB + sum-UCB
  * For candidates c in [0, n_cand):  k* (RBF cross kernel, never materialised in API
