@@ -78,6 +78,16 @@ _SIGNATURES = {
     "bo_mll_batched_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _dp, _dp, _dp,
                                    c_int, c_void_p, c_size_t, c_void_p]),
     "bo_hvi_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p, c_int, _dp, c_void_p]),
+    "bo_hvi_front_doubles": (c_size_t, [c_int, c_int]),
+    "bo_hvi_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "bo_hvi_prepare_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, _dp, c_void_p, c_size_t,
+                                   c_void_p]),
+    "bo_acquisition_hvi_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                       c_longlong, c_int, _dp, _dp, _dp, c_void_p, c_void_p, c_int, _dp, c_void_p]),
+    "bo_score_hvi_f64": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                 c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, _dp, _dp, _dp, _dp, c_double, c_void_p, c_void_p, c_int, _dp,
+                                 c_void_p, c_size_t, c_void_p]),
     "bo_grid_i64": (c_int, [c_void_p, c_longlong, POINTER(c_longlong), POINTER(c_longlong), c_int, c_longlong,
                             c_longlong, c_void_p]),
     "bo_kstar_dense_f64": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_int, c_void_p, c_int, c_int,

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import DeviceGP, _ptr, _stream, require_cuda, to_device
+from .engine import DeviceGP, HviFront, _ptr, _stream, require_cuda, to_device
 
 _F64 = torch.float64
 _selector = None
@@ -91,6 +91,25 @@ def exact_hvi_device(ucb: torch.Tensor, front: np.ndarray, reference_point: np.n
     _lib.check(lib.bo_hvi_f64(_ptr(out), _ptr(ucb), ucb.stride(0), n_cand, m, _ptr(f_dev), f.shape[0], pr,
                               _stream()))
     return out
+
+
+def ucb_and_exact_hvi_device(mu: torch.Tensor, var: torch.Tensor, prior_mean, prior_variance, betas,
+                             front: HviFront, want_ucb: bool = True):
+    """ONE fused per-candidate pass over (m, M) device arrays: standardise, UCB and the exact hypervolume
+    improvement of the UCB vector against a device-prepared front (bo_acquisition_hvi_f64) -- the fused form of
+    standardize_objectives + update_ucb + update_hypervolume_improvement (numba_kernels.py:538-570,
+    acquisition.py:55-108) with the exact HVI in place of the reference's sum.  Returns (ucb or None, hvi)."""
+    lib = _lib.load()
+    m, n_cand = mu.shape
+    ucb = torch.empty_like(mu) if want_ucb else None
+    hvi = torch.empty(n_cand, dtype=_F64, device=mu.device)
+    _, pm = _lib.host_doubles(prior_mean, m)
+    _, pv = _lib.host_doubles(prior_variance, m)
+    _, pb = _lib.host_doubles(betas, m)
+    _lib.check(lib.bo_acquisition_hvi_f64(None, None, _ptr(ucb), _ptr(hvi), _ptr(mu), _ptr(var), mu.stride(0), n_cand,
+                                          m, pm, pv, pb, _ptr(front.prepared), _ptr(front.count), front.n_points,
+                                          front.ref_ptr(), _stream()))
+    return ucb, hvi
 
 
 def update_exact_hypervolume_improvement(acquisition_values: np.ndarray, ucb: np.ndarray, front: np.ndarray,

@@ -15,8 +15,7 @@ import torch
 
 from . import config as cfg
 from . import distributed as bd
-from .acquisition import exact_hvi_device
-from .engine import DeviceGP, PinnedMirror, grid_candidates, require_cuda, to_device
+from .engine import DeviceGP, HviFront, PinnedMirror, grid_candidates, require_cuda, to_device
 from .numba_kernels import (compute_prior_mean, compute_prior_variance, initialize_lhs_integer,
                             optimize_hyperparams_mll)
 from .pareto import compute_pareto_front, is_pareto_efficient, print_pareto_analysis
@@ -44,13 +43,15 @@ class _Clock:
         return dict(zip(_TIMING_KEYS, spans))
 
 
-def _exact_hvi_scores(out, y_seen, prior_mean, prior_variance, reference_point):
-    """Opt-in acquisition: exact HVI of each UCB vector against the standardised observed front."""
+def _observed_front(y_seen, prior_mean, prior_variance, reference_point, device) -> HviFront:
+    """Opt-in acquisition: the front the exact HVI is measured against -- the observed objectives in the same
+    standardised units as the UCB vectors (numba_kernels.py:563-565), reference point = the standardised
+    ``reference_point`` pulled below every observation.  Dominance filtering, clipping and sorting happen on the
+    device (HviFront); the host only standardises the few evaluated rows."""
     scale = np.sqrt(prior_variance)
     y_std = (y_seen - prior_mean) / scale
-    front = y_std[is_pareto_efficient(y_std)]
     ref_std = np.minimum((np.asarray(reference_point, dtype=np.float64) - prior_mean) / scale, y_std.min(axis=0))
-    return exact_hvi_device(out["ucb"], front, ref_std)
+    return HviFront(y_std, ref_std, device)
 
 
 def _gather_shards(out, per_rank, n_total):
@@ -135,11 +136,11 @@ def optimize(x_vector, y_vector, kernel_matrices, k_star, mu_objectives, varianc
         torch.cuda.synchronize()
         clock.tick()
 
-        gp.score(candidates, betas, out=out)
+        # acquisition="exact_hvi": the epilogue of the SAME pass writes HVI(ucb vector) instead of sum-UCB
+        front = (_observed_front(seen_y, prior_mean, prior_variance, reference_point, device)
+                 if acquisition == "exact_hvi" else None)
+        gp.score(candidates, betas, out=out, hvi=front)
         score = out["acq"]
-        if acquisition == "exact_hvi":
-            score = _exact_hvi_scores(out, seen_y, prior_mean, prior_variance, reference_point)
-            out["acq"].copy_(score)
         if world == 1:
             _, picked = gp.select(candidates, score, gp.x, batch_size)
         else:

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libbo_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "factor.cu", "score.cu", "ozaki.cu", "select.cu", "mll.cu", "dense.cu"]
+SOURCES = ["api.cu", "gemm.cu", "factor.cu", "score.cu", "ozaki.cu", "select.cu", "hvi.cu", "mll.cu", "dense.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -9,6 +9,7 @@
 #include "dense.cuh"
 #include "factor.cuh"
 #include "gemm.cuh"
+#include "hvi.cuh"
 #include "mll.cuh"
 #include "ozaki.cuh"
 #include "score.cuh"
@@ -577,6 +578,75 @@ int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n
   BO_REQUIRE(hvi_dev && ucb_dev && ref_host && (front_dev || n_front == 0), "null pointer");
   BO_REQUIRE(m == 2 || m == 3, "exact HVI supports 2 or 3 objectives");
   return hvi(hvi_dev, ucb_dev, ld, n_cand, m, front_dev, n_front, ref_host, (cudaStream_t)stream);
+}
+
+size_t bo_hvi_front_doubles(int n_points, int m) { return hvi_front_doubles(n_points, m); }
+size_t bo_hvi_workspace_bytes(int n_points, int m) { return hvi_workspace_bytes(n_points, m); }
+
+int bo_hvi_prepare_f64(double* prepared_dev, int* n_front_dev, const double* points_dev, long long ld, int n_points,
+                       int m, const double* ref_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(prepared_dev && n_front_dev && ref_host && workspace_dev && (points_dev || n_points == 0), "null pointer");
+  BO_REQUIRE((m == 2 || m == 3) && ld >= m && n_points >= 0, "exact HVI supports 2 or 3 objectives");
+  return hvi_prepare(prepared_dev, n_front_dev, points_dev, ld, n_points, m, ref_host, workspace_dev, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+static int make_hvi_spec(HviSpec* spec, const double* prepared_dev, const int* n_front_dev, int n_points, int m,
+                         const double* ref_host) {
+  BO_REQUIRE(prepared_dev && n_front_dev && ref_host, "null pointer (prepared front)");
+  BO_REQUIRE(m == 2 || m == 3, "exact HVI supports 2 or 3 objectives");
+  spec->prepared = prepared_dev;
+  spec->n_front = n_front_dev;
+  spec->cap = n_points > 0 ? n_points : 1;
+  for (int o = 0; o < 3; ++o) spec->ref[o] = o < m ? ref_host[o] : 0.0;
+  return BO_OK;
+}
+
+int bo_acquisition_hvi_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* hvi_dev,
+                           const double* mu_dev, const double* var_dev, long long ld, long long n_cand, int m,
+                           const double* prior_mean_host, const double* prior_variance_host,
+                           const double* betas_host, const double* prepared_dev, const int* n_front_dev,
+                           int n_points, const double* ref_host, void* stream) {
+  BO_REQUIRE(mu_dev && var_dev && prior_mean_host && prior_variance_host && betas_host, "null pointer");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, nullptr, betas_host);
+  if (rc) return rc;
+  HviSpec spec;
+  rc = make_hvi_spec(&spec, prepared_dev, n_front_dev, n_points, m, ref_host);
+  if (rc) return rc;
+  return acquisition_hvi(std_mu_dev, std_var_dev, ucb_dev, hvi_dev, mu_dev, var_dev, ld, n_cand, m, hp, spec,
+                         (cudaStream_t)stream);
+}
+
+int bo_score_hvi_f64(int engine, double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev,
+                     double* ucb_dev, double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc,
+                     long long n_cand, const double* x_dev, int ldx, int n, int d, int m, const void* factor_dev,
+                     const double* wscale_dev, const double* alpha_dev, const double* prior_mean_host,
+                     const double* prior_variance_host, const double* length_scales_host, const double* betas_host,
+                     double min_variance, const double* prepared_dev, const int* n_front_dev, int n_points,
+                     const double* ref_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(engine == 0 || engine == 1, "engine: 0 = FP64 DMMA, 1 = INT8 tensor cores");
+  BO_REQUIRE(cand_dev && x_dev && factor_dev && alpha_dev && workspace_dev && (engine == 0 || wscale_dev),
+             "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host && betas_host,
+             "null hyper-parameter pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(n >= 1 && d >= 1 && d <= BO_MAX_DIMS && ldc >= d && ld_out >= n_cand, "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, betas_host);
+  if (rc) return rc;
+  ScoreOutputs out;
+  out.mu = mu_dev; out.var = var_dev; out.std_mu = std_mu_dev; out.std_var = std_var_dev;
+  out.ucb = ucb_dev; out.acq = acq_dev; out.ld = ld_out;
+  rc = make_hvi_spec(&out.hvi, prepared_dev, n_front_dev, n_points, m, ref_host);
+  if (rc) return rc;
+  if (engine == 0)
+    return score_candidates(out, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, m,
+                            static_cast<const double*>(factor_dev), alpha_dev, hp, min_variance, workspace_dev,
+                            workspace_bytes, (cudaStream_t)stream);
+  return oz_score_candidates(out, cand_dev, cand_kind, ldc, n_cand, x_dev, ldx, n, d, m,
+                             static_cast<const unsigned char*>(factor_dev), wscale_dev, alpha_dev, hp, min_variance,
+                             workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
 int bo_grid_i64(long long* out_dev, long long ld, const long long* lo_host, const long long* hi_host, int d,

@@ -1,0 +1,198 @@
+// hvi.cu -- preparation of the Pareto front on the device and the fused UCB + exact-HVI pass (see hvi.cuh).
+#include "hvi.cuh"
+
+#include "select.cuh"
+
+namespace bo {
+
+namespace {
+
+constexpr int HVI_SMEM_FRONT = 1024;  // m = 3: fronts up to this size are swept from shared memory
+
+// q[i][o] = max(p[i][o], ref[o])   (fmax drops NaN: a NaN coordinate is clipped to the reference point)
+__global__ void hvi_clip_kernel(double* __restrict__ q, const double* __restrict__ p, long long ld, int n, int m,
+                                double r0, double r1, double r2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  q[(long long)i * m + 0] = fmax(p[i * ld + 0], r0);
+  q[(long long)i * m + 1] = fmax(p[i * ld + 1], r1);
+  if (m == 3) q[(long long)i * m + 2] = fmax(p[i * ld + 2], r2);
+}
+
+// order of the prepared front: objective 0 desc, then objective 1 desc, (then objective 2 desc), then index asc
+__device__ __forceinline__ bool hvi_before(const double* __restrict__ q, int m, int j, int i) {
+  for (int o = 0; o < m; ++o) {
+    const double a = q[(long long)j * m + o], b = q[(long long)i * m + o];
+    if (a != b) return a > b;
+  }
+  return j < i;
+}
+
+// rank of every kept point among the kept points (counting sort by comparison: O(n^2), n is a few thousand at
+// most -- the evaluated points of a BO run), scatter into the prepared layout, count the live points
+__global__ void __launch_bounds__(256)
+    hvi_rank_scatter_kernel(double* __restrict__ prepared, int* __restrict__ n_front, const double* __restrict__ q,
+                            const uint8_t* __restrict__ mask, int n, int m, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int rank = 0, live = 0;
+  for (int j = 0; j < n; ++j) {
+    if (mask[j]) {
+      ++live;
+      if (j != i && hvi_before(q, m, j, i)) ++rank;
+    }
+  }
+  if (i == 0) *n_front = live;
+  if (!mask[i]) return;
+  for (int o = 0; o < m; ++o) prepared[(long long)o * cap + rank] = q[(long long)i * m + o];
+}
+
+// m = 2: S[i] = sum_{k<=i} (f0[k]-r0)(h[k]-h[k-1]); one warp, sequential carry (P is small, once per iteration)
+__global__ void hvi_prefix2_kernel(double* __restrict__ prepared, const int* __restrict__ n_front, int cap, double r0,
+                                   double r1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int P = *n_front;
+  const double* f0 = prepared;
+  const double* h = prepared + cap;
+  double* S = prepared + 2LL * cap;
+  double acc = 0.0, prev = r1;
+  for (int i = 0; i < P; ++i) {
+    acc += (f0[i] - r0) * (h[i] - prev);
+    prev = h[i];
+    S[i] = acc;
+  }
+}
+
+// m = 3: rank2[p] = position of p in objective-2-descending order (ties by position), zlev[rank] = objective 2
+__global__ void __launch_bounds__(256)
+    hvi_levels3_kernel(double* __restrict__ prepared, const int* __restrict__ n_front, int cap, double r2) {
+  const int P = *n_front;
+  const double* f2 = prepared + 2LL * cap;
+  double* zlev = prepared + 3LL * cap;
+  double* rank2 = prepared + 4LL * cap + 1;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) zlev[P] = r2;
+  if (p >= P) return;
+  int r = 0;
+  const double mine = f2[p];
+  for (int q = 0; q < P; ++q) {
+    const double v = f2[q];
+    r += (v > mine || (v == mine && q < p)) ? 1 : 0;
+  }
+  rank2[p] = (double)r;
+  zlev[r] = mine;
+}
+
+// standardise + UCB + exact HVI in one pass over (m, ld) mu / var (numba_kernels.py:538-570, acquisition.py:55-81,
+// then the exact hypervolume improvement instead of acquisition.py:104-108's sum)
+template <int MOBJ>
+__global__ void __launch_bounds__(256)
+    acquisition_hvi_kernel(double* __restrict__ smu_out, double* __restrict__ svar_out, double* __restrict__ ucb_out,
+                           double* __restrict__ hvi_out, const double* __restrict__ mu_in,
+                           const double* __restrict__ var_in, long long ld, long long n_cand, ObjParams hp,
+                           HviSpec spec) {
+  __shared__ double sf0[MOBJ == 3 ? HVI_SMEM_FRONT : 1], sf1[MOBJ == 3 ? HVI_SMEM_FRONT : 1];
+  __shared__ double szl[MOBJ == 3 ? HVI_SMEM_FRONT + 1 : 1], srk[MOBJ == 3 ? HVI_SMEM_FRONT : 1];
+  const int P = *spec.n_front;
+  const int cap = spec.cap;
+  const double* f0 = spec.prepared;
+  const double* f1 = spec.prepared + cap;
+  const double* zlev = spec.prepared + 3LL * cap;
+  const double* rank2 = spec.prepared + 4LL * cap + 1;
+  if (MOBJ == 3 && P <= HVI_SMEM_FRONT) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      sf0[p] = f0[p];
+      sf1[p] = f1[p];
+      srk[p] = rank2[p];
+      szl[p] = zlev[p];
+    }
+    if (threadIdx.x == 0) szl[P] = zlev[P];
+    __syncthreads();
+    f0 = sf0; f1 = sf1; zlev = szl; rank2 = srk;
+  }
+  double sd[MOBJ];
+#pragma unroll
+  for (int o = 0; o < MOBJ; ++o) sd[o] = sqrt(hp.prior_var[o]);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += stride) {
+    double u[MOBJ];
+#pragma unroll
+    for (int o = 0; o < MOBJ; ++o) {
+      const double smu = (mu_in[o * ld + i] - hp.prior_mean[o]) / sd[o];
+      const double svar = var_in[o * ld + i] / hp.prior_var[o];
+      // beta == 0 (raw vectors passed through bo_hvi_f64): no 0 * inf = NaN from an unused variance slot
+      u[o] = hp.beta[o] != 0.0 ? smu + hp.beta[o] * sqrt(fabs(svar)) : smu;
+      if (smu_out) smu_out[o * ld + i] = smu;
+      if (svar_out) svar_out[o * ld + i] = svar;
+      if (ucb_out) ucb_out[o * ld + i] = u[o];
+    }
+    double v;
+    if (MOBJ == 2) v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, P, spec.ref[0], spec.ref[1]);
+    else v = hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, zlev, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
+    if (hvi_out) hvi_out[i] = v;
+  }
+}
+
+}  // namespace
+
+size_t hvi_front_doubles(int n_points, int m) {
+  const size_t cap = n_points > 0 ? (size_t)n_points : 1;
+  return (m == 2 ? 3 * cap : 5 * cap + 1) + 2;  // see the layout in hvi.cuh
+}
+
+size_t hvi_workspace_bytes(int n_points, int m) {
+  const size_t n = n_points > 0 ? (size_t)n_points : 1;
+  return align256(n * m * sizeof(double)) + align256(n);  // clipped points + dominance mask
+}
+
+int hvi_prepare(double* prepared, int* n_front, const double* points, long long ld, int n_points, int m,
+                const double* ref, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < hvi_workspace_bytes(n_points, m)) {
+    set_error("hvi workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  if (n_points <= 0) {
+    BO_CUDA(cudaMemsetAsync(n_front, 0, sizeof(int), stream));
+    if (m == 3) {  // zlev[0] = r2 closes the single slab of an empty front
+      const double r2 = ref[2];
+      BO_CUDA(cudaMemcpyAsync(prepared + 3, &r2, sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    return BO_OK;
+  }
+  const int cap = n_points;
+  double* q = static_cast<double*>(workspace);
+  uint8_t* mask = reinterpret_cast<uint8_t*>(static_cast<unsigned char*>(workspace) +
+                                             align256((size_t)n_points * m * sizeof(double)));
+  const unsigned blocks = (unsigned)((n_points + 255) / 256);
+  hvi_clip_kernel<<<blocks, 256, 0, stream>>>(q, points, ld, n_points, m, ref[0], ref[1], m == 3 ? ref[2] : 0.0);
+  BO_LAUNCH_CHECK("hvi_clip_kernel");
+  int rc = pareto_mask(mask, q, m, n_points, q, m, n_points, m, stream);  // warp-ballot dominance kernel (select.cu)
+  if (rc) return rc;
+  hvi_rank_scatter_kernel<<<blocks, 256, 0, stream>>>(prepared, n_front, q, mask, n_points, m, cap);
+  BO_LAUNCH_CHECK("hvi_rank_scatter_kernel");
+  if (m == 2) {
+    hvi_prefix2_kernel<<<1, 32, 0, stream>>>(prepared, n_front, cap, ref[0], ref[1]);
+    BO_LAUNCH_CHECK("hvi_prefix2_kernel");
+  } else {
+    hvi_levels3_kernel<<<blocks, 256, 0, stream>>>(prepared, n_front, cap, ref[2]);
+    BO_LAUNCH_CHECK("hvi_levels3_kernel");
+  }
+  return BO_OK;
+}
+
+int acquisition_hvi(double* smu, double* svar, double* ucb, double* hvi_out, const double* mu, const double* var,
+                    long long ld, long long n_cand, int m, const ObjParams& hp, const HviSpec& spec,
+                    cudaStream_t stream) {
+  if (n_cand <= 0) return BO_OK;
+  long long blocks = (n_cand + 255) / 256;
+  const long long cap = 32LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  if (m == 2)
+    acquisition_hvi_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, hvi_out, mu, var, ld, n_cand, hp, spec);
+  else
+    acquisition_hvi_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, hvi_out, mu, var, ld, n_cand, hp, spec);
+  BO_LAUNCH_CHECK("acquisition_hvi_kernel");
+  return BO_OK;
+}
+
+}  // namespace bo

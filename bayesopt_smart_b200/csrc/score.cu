@@ -295,15 +295,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------- finalize
-__global__ void finalize_kernel(double* __restrict__ mu_out, double* __restrict__ var_out,
-                                double* __restrict__ smu_out, double* __restrict__ svar_out,
-                                double* __restrict__ ucb_out, double* __restrict__ acq_out, long long ld_out,
-                                long long cand0, long long n_cand, const double* __restrict__ part,
-                                const double* __restrict__ meandot, long long ld_chunk, int chunk_cands, int nb, int m,
-                                ObjParams hp, double min_variance) {
-  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long gi = cand0 + li;
-  if (li >= chunk_cands || gi >= n_cand) return;
+// a4..a8 for one candidate from the partial sums; returns sum-UCB and leaves the UCB vector in u[]
+__device__ __forceinline__ double finalize_candidate(double* __restrict__ mu_out, double* __restrict__ var_out,
+                                                     double* __restrict__ smu_out, double* __restrict__ svar_out,
+                                                     double* __restrict__ ucb_out, long long ld_out, long long gi,
+                                                     long long li, const double* __restrict__ part,
+                                                     const double* __restrict__ meandot, long long ld_chunk, int nb,
+                                                     int m, const ObjParams& hp, double min_variance, double* u) {
   double acq = 0.0;  // sequential sum from 0.0 (acquisition.py:108)
   for (int o = 0; o < m; ++o) {
     double q = 0.0;
@@ -314,13 +312,70 @@ __global__ void finalize_kernel(double* __restrict__ mu_out, double* __restrict_
     const double svar = var / hp.prior_var[o];                                // :568-570
     const double ucb = smu + hp.beta[o] * sqrt(fabs(svar));                   // acquisition.py:52
     acq = acq + ucb;
+    u[o] = ucb;
     if (mu_out) mu_out[o * ld_out + gi] = mu;
     if (var_out) var_out[o * ld_out + gi] = var;
     if (smu_out) smu_out[o * ld_out + gi] = smu;
     if (svar_out) svar_out[o * ld_out + gi] = svar;
     if (ucb_out) ucb_out[o * ld_out + gi] = ucb;
   }
+  return acq;
+}
+
+__global__ void finalize_kernel(double* __restrict__ mu_out, double* __restrict__ var_out,
+                                double* __restrict__ smu_out, double* __restrict__ svar_out,
+                                double* __restrict__ ucb_out, double* __restrict__ acq_out, long long ld_out,
+                                long long cand0, long long n_cand, const double* __restrict__ part,
+                                const double* __restrict__ meandot, long long ld_chunk, int chunk_cands, int nb, int m,
+                                ObjParams hp, double min_variance) {
+  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gi = cand0 + li;
+  if (li >= chunk_cands || gi >= n_cand) return;
+  double u[BO_MAX_OBJECTIVES];
+  const double acq = finalize_candidate(mu_out, var_out, smu_out, svar_out, ucb_out, ld_out, gi, li, part, meandot,
+                                        ld_chunk, nb, m, hp, min_variance, u);
   if (acq_out) acq_out[gi] = acq;
+}
+
+// opt-in exact mode: the same epilogue, but the acquisition value is the exact hypervolume improvement of the UCB
+// vector against the prepared front (hvi.cuh) -- UCB and HVI in ONE per-candidate pass, the UCB array is not
+// re-read from HBM.  m = 3 fronts of up to 1024 points are staged in shared memory.
+template <int MOBJ>
+__global__ void __launch_bounds__(256)
+    finalize_hvi_kernel(double* __restrict__ mu_out, double* __restrict__ var_out, double* __restrict__ smu_out,
+                        double* __restrict__ svar_out, double* __restrict__ ucb_out, double* __restrict__ acq_out,
+                        long long ld_out, long long cand0, long long n_cand, const double* __restrict__ part,
+                        const double* __restrict__ meandot, long long ld_chunk, int chunk_cands, int nb,
+                        ObjParams hp, double min_variance, HviSpec spec) {
+  constexpr int SM = MOBJ == 3 ? 1024 : 1;
+  __shared__ double sf0[SM], sf1[SM], szl[SM + 1], srk[SM];
+  const int P = *spec.n_front;
+  const int cap = spec.cap;
+  const double* f0 = spec.prepared;
+  const double* f1 = spec.prepared + cap;
+  const double* zlev = spec.prepared + 3LL * cap;
+  const double* rank2 = spec.prepared + 4LL * cap + 1;
+  if (MOBJ == 3 && P <= SM) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      sf0[p] = f0[p];
+      sf1[p] = f1[p];
+      srk[p] = rank2[p];
+      szl[p] = zlev[p];
+    }
+    if (threadIdx.x == 0) szl[P] = zlev[P];
+    __syncthreads();
+    f0 = sf0; f1 = sf1; zlev = szl; rank2 = srk;
+  }
+  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gi = cand0 + li;
+  if (li >= chunk_cands || gi >= n_cand) return;
+  double u[BO_MAX_OBJECTIVES];
+  finalize_candidate(mu_out, var_out, smu_out, svar_out, ucb_out, ld_out, gi, li, part, meandot, ld_chunk, nb, MOBJ, hp,
+                     min_variance, u);
+  double v;
+  if (MOBJ == 2) v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, P, spec.ref[0], spec.ref[1]);
+  else v = hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, zlev, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
+  if (acq_out) acq_out[gi] = v;
 }
 
 // stand-alone a6..a8 on existing arrays (HBM bound: reads 2m, writes up to 3m+1 doubles per candidate).
@@ -451,10 +506,22 @@ int finalize_chunk(const ScoreOutputs& out, long long cand0, long long n_cand, c
   // bytes per candidate: (nb + 1) m partials / mean dots read, n_out m + 1 doubles written
   ProfileScope prof_scope(stream, BO_PROF_FINALIZE,
                           (double)chunk_cands * 8.0 * ((double)(nb + 1) * m + (double)n_out * m + (out.acq ? 1 : 0)));
-  finalize_kernel<<<(chunk_cands + 255) / 256, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb,
-                                                                 out.acq, out.ld, cand0, n_cand, part, meandot,
-                                                                 ld_chunk, chunk_cands, nb, m, hp, min_variance);
-  BO_LAUNCH_CHECK("finalize_kernel");
+  const unsigned grid = (unsigned)((chunk_cands + 255) / 256);
+  if (out.hvi.prepared && m == 2) {
+    finalize_hvi_kernel<2><<<grid, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld,
+                                                     cand0, n_cand, part, meandot, ld_chunk, chunk_cands, nb, hp,
+                                                     min_variance, out.hvi);
+    BO_LAUNCH_CHECK("finalize_hvi_kernel");
+  } else if (out.hvi.prepared && m == 3) {
+    finalize_hvi_kernel<3><<<grid, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld,
+                                                     cand0, n_cand, part, meandot, ld_chunk, chunk_cands, nb, hp,
+                                                     min_variance, out.hvi);
+    BO_LAUNCH_CHECK("finalize_hvi_kernel");
+  } else {
+    finalize_kernel<<<grid, 256, 0, stream>>>(out.mu, out.var, out.std_mu, out.std_var, out.ucb, out.acq, out.ld, cand0,
+                                              n_cand, part, meandot, ld_chunk, chunk_cands, nb, m, hp, min_variance);
+    BO_LAUNCH_CHECK("finalize_kernel");
+  }
   return BO_OK;
 }
 

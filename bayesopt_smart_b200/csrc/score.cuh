@@ -1,6 +1,7 @@
 // score.cuh -- host interface of the per-candidate scoring pass (score.cu).
 #pragma once
 #include "common.cuh"
+#include "hvi.cuh"
 
 namespace bo {
 
@@ -17,6 +18,7 @@ size_t score_workspace_bytes(const ScorePlan& p);
 struct ScoreOutputs {
   double *mu = nullptr, *var = nullptr, *std_mu = nullptr, *std_var = nullptr, *ucb = nullptr, *acq = nullptr;
   long long ld = 0;
+  HviSpec hvi;  // hvi.prepared != nullptr: acq = exact hypervolume improvement of the UCB vector (opt-in mode)
 };
 
 int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, int ldc, long long n_cand,

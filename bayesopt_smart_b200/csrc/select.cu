@@ -10,6 +10,8 @@
 
 #include <stdlib.h>
 
+#include "hvi.cuh"
+
 namespace bo {
 
 namespace {
@@ -507,8 +509,31 @@ int hvi(double* out, const double* ucb, long long ld, long long n_cand, int m, c
         const double* ref, cudaStream_t stream) {
   if (n_cand <= 0) return BO_OK;
   if (n_front > HVI_MAX_FRONT) {
-    set_error("front larger than %d points", HVI_MAX_FRONT);
-    return BO_ERR_INVALID;
+    // larger fronts go through the prepared-front path (hvi.cu: no cap).  This entry point has no workspace
+    // argument, so the few KB of front tables are stream-ordered temporaries.
+    double* prepared = nullptr;
+    int* count = nullptr;
+    void* ws = nullptr;
+    const size_t ws_bytes = hvi_workspace_bytes(n_front, m);
+    BO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prepared), hvi_front_doubles(n_front, m) * sizeof(double), stream));
+    BO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&count), sizeof(int), stream));
+    BO_CUDA(cudaMallocAsync(&ws, ws_bytes, stream));
+    int rc = hvi_prepare(prepared, count, front, m, n_front, m, ref, ws, ws_bytes, stream);
+    if (rc == BO_OK) {
+      ObjParams unit;  // (u - 0) / sqrt(1) + 0 * sqrt(|.|) = u: the "UCB" of the fused kernel is the given vector
+      memset(&unit, 0, sizeof(unit));
+      for (int o = 0; o < BO_MAX_OBJECTIVES; ++o) unit.prior_var[o] = 1.0;
+      HviSpec spec;
+      spec.prepared = prepared;
+      spec.n_front = count;
+      spec.cap = n_front;
+      for (int o = 0; o < 3; ++o) spec.ref[o] = o < m ? ref[o] : 0.0;
+      rc = acquisition_hvi(nullptr, nullptr, nullptr, out, ucb, ucb, ld, n_cand, m, unit, spec, stream);
+    }
+    cudaFreeAsync(ws, stream);
+    cudaFreeAsync(count, stream);
+    cudaFreeAsync(prepared, stream);
+    return rc;
   }
   const unsigned grid = (unsigned)((n_cand + 255) / 256);
   if (m == 2)

@@ -96,6 +96,42 @@ def candidate_kind(cand: torch.Tensor) -> int:
 VARIANCE_ENGINES = ("dmma", "int8")
 
 
+class HviFront:
+    """A Pareto front prepared ON THE DEVICE for the fused UCB + exact-HVI pass (bo_hvi_prepare_f64): points
+    clipped to the reference point, dominated points removed by the dominance kernel, sorted by objective 0
+    descending, plus the staircase prefix areas (m = 2) or objective-2 levels (m = 3).  No host sort, no host
+    synchronisation; ``count`` stays a device scalar."""
+
+    def __init__(self, points, reference_point, device=None):
+        device = device or require_cuda()
+        lib = _lib.load()
+        pts = to_device(np.asarray(points, dtype=np.float64) if not isinstance(points, torch.Tensor) else points,
+                        _F64, device)
+        if pts.dim() != 2 or pts.shape[1] not in (2, 3):
+            raise ValueError("exact HVI needs (n, 2) or (n, 3) points")
+        self.m = int(pts.shape[1])
+        self.n_points = int(pts.shape[0])
+        self.ref, pr = _lib.host_doubles(reference_point, self.m)
+        self.prepared = torch.empty(lib.bo_hvi_front_doubles(self.n_points, self.m), dtype=_F64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        ws_bytes = lib.bo_hvi_workspace_bytes(self.n_points, self.m)
+        ws = torch.empty(max(int(ws_bytes), 256), dtype=torch.uint8, device=device)
+        _lib.check(lib.bo_hvi_prepare_f64(_ptr(self.prepared), _ptr(self.count), _ptr(pts) if self.n_points else None,
+                                          pts.stride(0) if self.n_points else self.m, self.n_points, self.m, pr,
+                                          _ptr(ws), ws_bytes, _stream()))
+        self._keep = (pts, ws)  # alive until the stream has consumed them
+
+    def ref_ptr(self):
+        return self.ref.ctypes.data_as(_lib._dp)
+
+    def points(self) -> np.ndarray:
+        """The prepared front as a host array (P, m), objective 0 descending (diagnostics / tests)."""
+        p = int(self.count.item())
+        cap = max(self.n_points, 1)
+        cols = [self.prepared[o * cap: o * cap + p].cpu().numpy() for o in range(self.m)]
+        return np.stack(cols, axis=1) if p else np.zeros((0, self.m))
+
+
 class DeviceGP:
     """GP factor + scorer living in HBM.  One instance per process / GPU.
 
@@ -232,11 +268,13 @@ class DeviceGP:
 
     # ------------------------------------------------------------------ score
     def score(self, candidates, betas, *, want=("mu", "var", "acq"), out: Optional[Dict[str, torch.Tensor]] = None,
-              min_variance: float = MIN_VARIANCE) -> Dict[str, torch.Tensor]:
-        """Posterior + UCB + sum-UCB for every candidate row.  Returns CUDA tensors.
+              min_variance: float = MIN_VARIANCE, hvi: Optional["HviFront"] = None) -> Dict[str, torch.Tensor]:
+        """Posterior + UCB + acquisition for every candidate row.  Returns CUDA tensors.
 
         ``want`` picks which arrays are written: mu, var, std_mu, std_var, ucb (each (m, M)), acq (M,).
-        ``out`` may carry preallocated tensors under the same keys.
+        ``out`` may carry preallocated tensors under the same keys.  ``acq`` is the reference's sum-UCB
+        (acquisition.py:104-108) unless ``hvi`` carries a prepared front: then the epilogue of the same pass
+        writes the exact hypervolume improvement of each UCB vector (opt-in mode, m = 2 or 3).
         """
         if self.wpack is None:
             raise _lib.BoError("DeviceGP.score called before fit")
@@ -246,6 +284,8 @@ class DeviceGP:
         kind = candidate_kind(cand)
         n_cand = cand.shape[0]
         m = self.m
+        if hvi is not None and hvi.m != m:
+            raise ValueError(f"the prepared front has {hvi.m} objectives, the model {m}")
         res: Dict[str, Optional[torch.Tensor]] = {}
         for key in ("mu", "var", "std_mu", "std_var", "ucb", "acq"):
             if out is not None and key in out:
@@ -259,23 +299,27 @@ class DeviceGP:
         _, pv = _lib.host_doubles(self.prior_variance, m)
         _, pl = _lib.host_doubles(self.length_scales, m)
         bet, pb = _lib.host_doubles(betas, m)
-        if self.variance_engine == "int8":
+        int8 = self.variance_engine == "int8"
+        if int8:
             ws_bytes = self.lib.bo_score_i8_workspace_bytes(self.n, m, n_cand)
             ws = self.ws.get("score_i8", ws_bytes, self.device)
-            _lib.check(self.lib.bo_score_i8(_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]),
-                                            _ptr(res["std_var"]), _ptr(res["ucb"]), _ptr(res["acq"]), n_cand,
-                                            _ptr(cand), kind, cand.stride(0), n_cand, _ptr(self.x),
-                                            self.x.stride(0), self.n, self.d, m, _ptr(self.wq), _ptr(self.wscale),
-                                            _ptr(self.alpha), pm, pv, pl, pb, float(min_variance), _ptr(ws),
-                                            ws_bytes, _stream()))
-            return {k: v for k, v in res.items() if v is not None}
-        ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
-        ws = self.ws.get("score", ws_bytes, self.device)
-        _lib.check(self.lib.bo_score_f64(_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]), _ptr(res["std_var"]),
-                                         _ptr(res["ucb"]), _ptr(res["acq"]), n_cand, _ptr(cand), kind,
-                                         cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0), self.n, self.d, m,
-                                         _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl, pb, float(min_variance),
-                                         _ptr(ws), ws_bytes, _stream()))
+        else:
+            ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
+            ws = self.ws.get("score", ws_bytes, self.device)
+        outs = (_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]), _ptr(res["std_var"]), _ptr(res["ucb"]),
+                _ptr(res["acq"]), n_cand, _ptr(cand), kind, cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0),
+                self.n, self.d, m)
+        if hvi is not None:
+            _lib.check(self.lib.bo_score_hvi_f64(1 if int8 else 0, *outs, _ptr(self.wq) if int8 else _ptr(self.wpack),
+                                                 _ptr(self.wscale) if int8 else None, _ptr(self.alpha), pm, pv, pl, pb,
+                                                 float(min_variance), _ptr(hvi.prepared), _ptr(hvi.count),
+                                                 hvi.n_points, hvi.ref_ptr(), _ptr(ws), ws_bytes, _stream()))
+        elif int8:
+            _lib.check(self.lib.bo_score_i8(*outs, _ptr(self.wq), _ptr(self.wscale), _ptr(self.alpha), pm, pv, pl, pb,
+                                            float(min_variance), _ptr(ws), ws_bytes, _stream()))
+        else:
+            _lib.check(self.lib.bo_score_f64(*outs, _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl, pb,
+                                             float(min_variance), _ptr(ws), ws_bytes, _stream()))
         return {k: v for k, v in res.items() if v is not None}
 
     # ------------------------------------------------------------------ select

@@ -220,11 +220,47 @@ int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const doub
 
 /* ------------------------------------------------ opt-in: exact hypervolume improvement
  * hvi[i] = HV(front U {u_i}) - HV(front), u_i = (ucb[0][i], .., ucb[m-1][i]), m = 2 or 3.
- * `front_dev` is (n_front <= 1024, m) row-major, sorted by objective 0 DESCENDING (points
- * below `ref` are clipped to it; dominated points are harmless).  No reference
+ * `front_dev` is (n_front, m) row-major, sorted by objective 0 DESCENDING (points below `ref` are clipped to
+ * it; dominated points are harmless); fronts of more than 1024 points are read from global memory instead of
+ * shared memory (no cap).  Second pass over an existing ucb array: the fused forms are below.  No reference
  * counterpart (the reference's "HVI" is sum-UCB, acquisition.py:104-108).           */
 int bo_hvi_f64(double* hvi_dev, const double* ucb_dev, long long ld, long long n_cand, int m,
                const double* front_dev, int n_front, const double* ref_host, void* stream);
+
+/* ------------------------------- opt-in: UCB + exact HVI as ONE fused per-candidate pass
+ * BASELINE.json's north star: "UCB and 2-objective and 3-objective HVI become one fused per-candidate kernel
+ * against a sorted Pareto front held in shared memory".  The front is PREPARED on the device (no host sort):
+ *   bo_hvi_prepare_f64: raw points (n_points, ld) row-major (e.g. the standardised observed objectives) ->
+ *     clipped to `ref`, dominated points removed (the warp-ballot dominance kernel of a10), sorted by objective 0
+ *     descending, plus the per-front tables the evaluation needs (m = 2: staircase prefix areas, which make the
+ *     2-objective HVI two binary searches + O(1) for any front size; m = 3: objective-2 levels and ranks, swept
+ *     from shared memory up to 1024 points and from global memory beyond).  prepared_dev holds
+ *     bo_hvi_front_doubles(n_points, m) doubles, n_front_dev one int.  Asynchronous, no host synchronisation.
+ *   bo_acquisition_hvi_f64: stand-alone fused pass standardise + UCB + HVI over existing (m, ld) mu / var arrays
+ *     (replaces standardize_objectives + update_ucb + update_hypervolume_improvement, numba_kernels.py:538-570,
+ *     acquisition.py:55-108, with the exact HVI in place of the sum).  Outputs may be NULL.
+ *   bo_score_hvi_f64: the whole scoring pass (same contract as bo_score_f64 / bo_score_i8) whose epilogue writes
+ *     acq = HVI(ucb vector) -- the UCB array never makes an extra trip through HBM.  engine 0: factor_dev = wpack
+ *     (FP64 DMMA engine), wscale_dev NULL; engine 1: factor_dev = the int8 digit planes wq, wscale_dev their
+ *     scales.  workspace sized by bo_score_workspace_bytes / bo_score_i8_workspace_bytes.
+ * m = 2 or 3.  `n_points` passed to the evaluation calls must be the value given to bo_hvi_prepare_f64.
+ * No reference counterpart (its "HVI" is sum-UCB); specification: oracle/gp_oracle.py exact_hvi.           */
+size_t bo_hvi_front_doubles(int n_points, int m);
+size_t bo_hvi_workspace_bytes(int n_points, int m);
+int bo_hvi_prepare_f64(double* prepared_dev, int* n_front_dev, const double* points_dev, long long ld, int n_points,
+                       int m, const double* ref_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+int bo_acquisition_hvi_f64(double* std_mu_dev, double* std_var_dev, double* ucb_dev, double* hvi_dev,
+                           const double* mu_dev, const double* var_dev, long long ld, long long n_cand, int m,
+                           const double* prior_mean_host, const double* prior_variance_host,
+                           const double* betas_host, const double* prepared_dev, const int* n_front_dev,
+                           int n_points, const double* ref_host, void* stream);
+int bo_score_hvi_f64(int engine, double* mu_dev, double* var_dev, double* std_mu_dev, double* std_var_dev,
+                     double* ucb_dev, double* acq_dev, long long ld_out, const void* cand_dev, int cand_kind, int ldc,
+                     long long n_cand, const double* x_dev, int ldx, int n, int d, int m, const void* factor_dev,
+                     const double* wscale_dev, const double* alpha_dev, const double* prior_mean_host,
+                     const double* prior_variance_host, const double* length_scales_host, const double* betas_host,
+                     double min_variance, const double* prepared_dev, const int* n_front_dev, int n_points,
+                     const double* ref_host, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------ candidate set on the device
  * Rows [row0, row0 + rows) of the integer Cartesian grid prod_k [lo_k, hi_k) in C order -- what the reference
