@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbo_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "bo_b200.h")
 
-BO_OK, BO_ERR_INVALID, BO_ERR_CUDA, BO_ERR_NOT_PD, BO_ERR_WORKSPACE = 0, 1, 2, 3, 4
+BO_OK, BO_ERR_INVALID, BO_ERR_CUDA, BO_ERR_NOT_PD, BO_ERR_WORKSPACE, BO_ERR_GUARD = 0, 1, 2, 3, 4, 5
 BO_CAND_F64, BO_CAND_I64 = 0, 1
 BO_MAX_OBJECTIVES, BO_MAX_DIMS, BO_MAX_TOPK, BO_TILE = 4, 16, 1024, 128
 BO_MAX_APPEND = 32
@@ -24,6 +24,10 @@ BO_PROF_CONTRACTION, BO_PROF_KSTAR, BO_PROF_FINALIZE, BO_PROF_TOPK, BO_PROF_FIT 
 
 class BoError(RuntimeError):
     """A libbo_b200 call returned a non-zero status."""
+
+
+class Int8GuardError(BoError):
+    """The INT8 variance engine's sampled cross-check against the FP64 engine exceeded its tolerance."""
 
 
 _dp = POINTER(c_double)
@@ -55,6 +59,10 @@ _SIGNATURES = {
     "bo_score_i8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                             c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             _dp, _dp, _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
+    "bo_i8_guard_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_longlong, c_longlong]),
+    "bo_i8_guard_f64": (c_int, [_dp, c_void_p, c_int, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int, c_int,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, _dp, _dp, _dp, c_double, c_double,
+                                c_void_p, c_size_t, c_void_p]),
     "bo_i8_peak_tops": (c_int, [_dp, c_double, c_void_p]),
     "bo_i8_kstar_digits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, _dp, _dp, c_void_p]),
@@ -138,6 +146,8 @@ def check(rc: int) -> None:
     msg = load().bo_last_error().decode("utf-8", "replace")
     if rc == BO_ERR_NOT_PD:
         raise np.linalg.LinAlgError(msg or "Matrix is not positive definite")
+    if rc == BO_ERR_GUARD:
+        raise Int8GuardError(msg)
     raise BoError(f"libbo_b200 error {rc}: {msg}")
 
 

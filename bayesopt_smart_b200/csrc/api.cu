@@ -464,6 +464,29 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
                              alpha_dev, hp, min_variance, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t bo_i8_guard_workspace_bytes(int n, int m, int d, long long n_cand, long long stride) {
+  if (stride < 1) stride = 1;
+  return oz_guard_workspace_bytes(n, m, d, n_cand, stride);
+}
+
+int bo_i8_guard_f64(double* worst_host, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
+                    long long stride, const double* x_dev, int ldx, int n, int d, int m, const uint8_t* wq_dev,
+                    const double* wscale_dev, const double* wpack_dev, const double* alpha_dev,
+                    const double* prior_mean_host, const double* prior_variance_host,
+                    const double* length_scales_host, double min_variance, double tol, void* workspace_dev,
+                    size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(cand_dev && x_dev && wq_dev && wscale_dev && wpack_dev && alpha_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host, "null hyper-parameter pointer");
+  BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
+  BO_REQUIRE(n >= 1 && n <= OZ_MAX_N && d >= 1 && d <= BO_MAX_DIMS && ldc >= d && n_cand >= 1 && stride >= 1,
+             "bad sizes");
+  ObjParams hp;
+  int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, nullptr);
+  if (rc) return rc;
+  return oz_guard(worst_host, cand_dev, cand_kind, ldc, n_cand, stride, x_dev, ldx, n, d, m, wq_dev, wscale_dev,
+                  wpack_dev, alpha_dev, hp, min_variance, tol, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
 int bo_i8_peak_tops(double* tops_host, double seconds, void* stream) {
   BO_REQUIRE(tops_host && seconds > 0.0 && seconds < 5.0, "bad arguments");
   return oz_peak_tops(tops_host, seconds, (cudaStream_t)stream);

@@ -802,6 +802,108 @@ int oz_peak_tops(double* tops, double seconds, cudaStream_t st) {
   return BO_OK;
 }
 
+// ------------------------------------------------------------------------------------------- sampled guard
+namespace {
+
+__device__ __forceinline__ long long guard_pos(long long j, long long stride, long long n_cand) {
+  const unsigned h = (unsigned)j * 2654435761u;  // hashed offset inside the window: no aliasing with grid periods
+  long long p = j * stride + (long long)((h >> 8) % (unsigned long long)stride);
+  return p < n_cand ? p : n_cand - 1;
+}
+
+template <typename CT>
+__global__ void guard_gather_kernel(double* __restrict__ out, const CT* __restrict__ cand, int ldc, long long n_cand,
+                                    long long stride, int n_sample, int d) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_sample) return;
+  const long long p = guard_pos(j, stride, n_cand);
+  for (int k = 0; k < d; ++k) out[(long long)j * d + k] = (double)cand[p * ldc + k];
+}
+
+// worst[0] = max over the sample of |var_int8 - var_fp64| / prior_variance  (NaN counts as +inf)
+__global__ void guard_compare_kernel(double* __restrict__ worst, const double* __restrict__ va,
+                                     const double* __restrict__ vb, int n_sample, int m, ObjParams hp) {
+  __shared__ double red[256];
+  double mx = 0.0;
+  for (int e = threadIdx.x; e < n_sample * m; e += blockDim.x) {
+    const int o = e / n_sample;
+    const double dv = fabs(va[e] - vb[e]) / hp.prior_var[o];
+    mx = (dv != dv) ? __longlong_as_double(0x7ff0000000000000ll) : fmax(mx, dv);
+  }
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) worst[0] = red[0];
+}
+
+int guard_samples(long long n_cand, long long stride) {
+  long long s = (n_cand + stride - 1) / stride;
+  if (s > 65536) s = 65536;
+  return (int)(s < 1 ? 1 : s);
+}
+
+}  // namespace
+
+size_t oz_guard_workspace_bytes(int n, int m, int d, long long n_cand, long long stride) {
+  const int S = guard_samples(n_cand, stride);
+  return align256((size_t)S * d * 8) + 2 * align256((size_t)m * S * 8) + 256 +
+         align256(oz_workspace_bytes(make_oz_plan(n, m, S))) + align256(score_workspace_bytes(make_score_plan(n, m, S)));
+}
+
+int oz_guard(double* worst_host, const void* cand, int cand_kind, int ldc, long long n_cand, long long stride,
+             const double* x, int ldx, int n, int d, int m, const unsigned char* wq, const double* wscale,
+             const double* wpack, const double* alpha, const ObjParams& hp, double min_variance, double tol,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < oz_guard_workspace_bytes(n, m, d, n_cand, stride)) {
+    set_error("int8 guard workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  const int S = guard_samples(n_cand, stride);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  size_t off = 0;
+  double* sample = reinterpret_cast<double*>(ws + off);  off += align256((size_t)S * d * 8);
+  double* va = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
+  double* vb = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
+  double* worst = reinterpret_cast<double*>(ws + off);   off += 256;
+  void* ws_i8 = ws + off;
+  const size_t ws_i8_bytes = oz_workspace_bytes(make_oz_plan(n, m, S));
+  off += align256(ws_i8_bytes);
+  void* ws_f64 = ws + off;
+  const size_t ws_f64_bytes = score_workspace_bytes(make_score_plan(n, m, S));
+  if (cand_kind == BO_CAND_I64)
+    guard_gather_kernel<long long><<<(S + 255) / 256, 256, 0, stream>>>(sample, static_cast<const long long*>(cand), ldc,
+                                                                        n_cand, stride, S, d);
+  else
+    guard_gather_kernel<double><<<(S + 255) / 256, 256, 0, stream>>>(sample, static_cast<const double*>(cand), ldc,
+                                                                     n_cand, stride, S, d);
+  BO_LAUNCH_CHECK("guard_gather_kernel");
+  ScoreOutputs oa, ob;
+  oa.var = va; oa.ld = S;
+  ob.var = vb; ob.ld = S;
+  // a candidate's result does not depend on the chunking, so these are bit for bit the numbers of the main pass
+  int rc = oz_score_candidates(oa, sample, BO_CAND_F64, d, S, x, ldx, n, d, m, wq, wscale, alpha, hp, min_variance,
+                               ws_i8, ws_i8_bytes, stream);
+  if (rc) return rc;
+  rc = score_candidates(ob, sample, BO_CAND_F64, d, S, x, ldx, n, d, m, wpack, alpha, hp, min_variance, ws_f64,
+                        ws_f64_bytes, stream);
+  if (rc) return rc;
+  guard_compare_kernel<<<1, 256, 0, stream>>>(worst, va, vb, S, m, hp);
+  BO_LAUNCH_CHECK("guard_compare_kernel");
+  double w = 0.0;
+  BO_CUDA(cudaMemcpyAsync(&w, worst, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  BO_CUDA(cudaStreamSynchronize(stream));
+  if (worst_host) *worst_host = w;
+  if (!(w <= tol)) {
+    set_error("int8 variance engine guard: |var_int8 - var_fp64| / prior_variance = %.3e exceeds %.3e on a sample of "
+              "%d candidates (no fallback: use variance_engine=\"dmma\")", w, tol, S);
+    return BO_ERR_GUARD;
+  }
+  return BO_OK;
+}
+
 OzPlan make_oz_plan(int n, int m, long long n_cand) {
   OzPlan p;
   p.npad = round_up(n, OZ_TM);

@@ -140,11 +140,20 @@ class DeviceGP:
     from the FP64 result).  ``BO_VARIANCE_ENGINE`` overrides the default.
     """
 
-    def __init__(self, device=None, variance_engine: Optional[str] = None):
+    def __init__(self, device=None, variance_engine: Optional[str] = None, int8_guard_tol: Optional[float] = None,
+                 int8_guard_stride: int = 4096):
         self.device = device or require_cuda()
         self.variance_engine = variance_engine or os.environ.get("BO_VARIANCE_ENGINE", "dmma")
         if self.variance_engine not in VARIANCE_ENGINES:
             raise ValueError(f"variance_engine must be one of {VARIANCE_ENGINES}, got {self.variance_engine!r}")
+        # INT8 engine: every score() cross-checks one candidate in `int8_guard_stride` against the FP64 engine and
+        # raises Int8GuardError -- no fallback -- if |d var| / prior_variance exceeds the tolerance (default: the 1e-9
+        # parity target).  BO_I8_GUARD=0 or int8_guard_tol <= 0 switches the check off.
+        if int8_guard_tol is None:
+            int8_guard_tol = 0.0 if os.environ.get("BO_I8_GUARD", "1") == "0" else 1e-9
+        self.int8_guard_tol = float(int8_guard_tol)
+        self.int8_guard_stride = max(1, int(int8_guard_stride))
+        self.last_guard_worst: Optional[float] = None  # largest sampled |d var| / prior_variance of the last score()
         self.wq: Optional[torch.Tensor] = None
         self.wscale: Optional[torch.Tensor] = None
         self.lib = _lib.load()
@@ -320,6 +329,16 @@ class DeviceGP:
         else:
             _lib.check(self.lib.bo_score_f64(*outs, _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl, pb,
                                              float(min_variance), _ptr(ws), ws_bytes, _stream()))
+        if int8 and self.int8_guard_tol > 0.0 and n_cand > 0:
+            gbytes = self.lib.bo_i8_guard_workspace_bytes(self.n, m, self.d, n_cand, self.int8_guard_stride)
+            gws = self.ws.get("i8_guard", gbytes, self.device)
+            worst = ctypes.c_double(0.0)
+            rc = self.lib.bo_i8_guard_f64(ctypes.byref(worst), _ptr(cand), kind, cand.stride(0), n_cand,
+                                          self.int8_guard_stride, _ptr(self.x), self.x.stride(0), self.n, self.d, m,
+                                          _ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack), _ptr(self.alpha), pm, pv,
+                                          pl, float(min_variance), self.int8_guard_tol, _ptr(gws), gbytes, _stream())
+            self.last_guard_worst = worst.value
+            _lib.check(rc)  # Int8GuardError: the caller decides (there is no silent switch to the FP64 engine)
         return {k: v for k, v in res.items() if v is not None}
 
     # ------------------------------------------------------------------ select

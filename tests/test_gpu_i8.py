@@ -249,3 +249,40 @@ def test_randomised_shapes_are_deterministic_and_within_tau(env):
     r = subprocess.run([sys.executable, os.path.join("tools", "oz_stress.py"), "40", "7"], cwd=root,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sampled_guard_passes_and_trips(env):
+    """the INT8 engine cross-checks one candidate in `stride` against the FP64 engine on
+    every score() and fails loudly -- no fallback -- when the difference exceeds the tolerance."""
+    DeviceGP, _lib = env["DeviceGP"], env["_lib"]
+    n, d, m = 700, 6, 2
+    x, y, mu0, var0 = orc.make_training_set("zdt1", n, d, seed=0)
+    ls, betas = np.full(m, 0.3), np.full(m, 2.0)
+    cand = np.random.default_rng(2).random((300_000, d))
+    gp = DeviceGP(variance_engine="int8")               # default: tolerance 1e-9, one candidate in 4096
+    gp.fit(x, y, mu0, var0, ls, n)
+    out = gp.score(cand, betas, want=("var", "acq"))
+    assert gp.last_guard_worst is not None and 0.0 < gp.last_guard_worst < 1e-10
+    # the sampled numbers are those of the main pass: re-derive the worst difference from the full arrays
+    ref = DeviceGP()
+    ref.fit(x, y, mu0, var0, ls, n)
+    full = ref.score(cand, betas, want=("var",))
+    dv = ((out["var"] - full["var"]).abs() / torch.tensor(var0, device="cuda")[:, None]).max().item()
+    assert gp.last_guard_worst <= dv <= 1e-10
+    # a tolerance below what the digit format delivers: the guard must fire
+    tight = DeviceGP(variance_engine="int8", int8_guard_tol=1e-15)
+    tight.fit(x, y, mu0, var0, ls, n)
+    with pytest.raises(_lib.Int8GuardError):
+        tight.score(cand, betas, want=("acq",))
+    assert tight.last_guard_worst > 1e-15
+    # a damaged INT8 factor (row scales off by 1e-4): caught at the default tolerance, FP64 engine untouched
+    gp.wscale[: 2 * 128] *= 1.0 + 1e-4
+    with pytest.raises(_lib.Int8GuardError):
+        gp.score(cand, betas, want=("acq",))
+    assert gp.last_guard_worst > 1e-9
+    # switched off explicitly: no check, no error
+    off = DeviceGP(variance_engine="int8", int8_guard_tol=0.0)
+    off.fit(x, y, mu0, var0, ls, n)
+    off.wscale[: 2 * 128] *= 1.0 + 1e-4
+    off.score(cand, betas, want=("acq",))
+    assert off.last_guard_worst is None
