@@ -60,9 +60,9 @@ _SIGNATURES = {
                             c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             _dp, _dp, _dp, _dp, c_double, c_void_p, c_size_t, c_void_p]),
     "bo_i8_guard_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_longlong, c_longlong]),
-    "bo_i8_guard_f64": (c_int, [_dp, c_void_p, c_int, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int, c_int,
-                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, _dp, _dp, _dp, c_double, c_double,
-                                c_void_p, c_size_t, c_void_p]),
+    "bo_i8_guard_f64": (c_int, [_dp, _dp, c_void_p, c_int, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, _dp, _dp, _dp, c_double,
+                                c_double, c_double, c_void_p, c_size_t, c_void_p]),
     "bo_i8_peak_tops": (c_int, [_dp, c_double, c_void_p]),
     "bo_i8_kstar_digits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, _dp, _dp, c_void_p]),

@@ -469,12 +469,12 @@ size_t bo_i8_guard_workspace_bytes(int n, int m, int d, long long n_cand, long l
   return oz_guard_workspace_bytes(n, m, d, n_cand, stride);
 }
 
-int bo_i8_guard_f64(double* worst_host, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
-                    long long stride, const double* x_dev, int ldx, int n, int d, int m, const uint8_t* wq_dev,
-                    const double* wscale_dev, const double* wpack_dev, const double* alpha_dev,
-                    const double* prior_mean_host, const double* prior_variance_host,
-                    const double* length_scales_host, double min_variance, double tol, void* workspace_dev,
-                    size_t workspace_bytes, void* stream) {
+int bo_i8_guard_f64(double* worst_host, double* tau_host, const void* cand_dev, int cand_kind, int ldc,
+                    long long n_cand, long long stride, const double* x_dev, int ldx, int n, int d, int m,
+                    const uint8_t* wq_dev, const double* wscale_dev, const double* wpack_dev,
+                    const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
+                    const double* length_scales_host, double jitter, double min_variance, double tol,
+                    void* workspace_dev, size_t workspace_bytes, void* stream) {
   BO_REQUIRE(cand_dev && x_dev && wq_dev && wscale_dev && wpack_dev && alpha_dev && workspace_dev, "null pointer");
   BO_REQUIRE(prior_mean_host && prior_variance_host && length_scales_host, "null hyper-parameter pointer");
   BO_REQUIRE(cand_kind == BO_CAND_F64 || cand_kind == BO_CAND_I64, "cand_kind");
@@ -483,8 +483,9 @@ int bo_i8_guard_f64(double* worst_host, const void* cand_dev, int cand_kind, int
   ObjParams hp;
   int rc = make_params(&hp, m, prior_mean_host, prior_variance_host, length_scales_host, nullptr);
   if (rc) return rc;
-  return oz_guard(worst_host, cand_dev, cand_kind, ldc, n_cand, stride, x_dev, ldx, n, d, m, wq_dev, wscale_dev,
-                  wpack_dev, alpha_dev, hp, min_variance, tol, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+  return oz_guard(worst_host, tau_host, cand_dev, cand_kind, ldc, n_cand, stride, x_dev, ldx, n, d, m, wq_dev,
+                  wscale_dev, wpack_dev, alpha_dev, hp, jitter, min_variance, tol, workspace_dev, workspace_bytes,
+                  (cudaStream_t)stream);
 }
 
 int bo_i8_peak_tops(double* tops_host, double seconds, void* stream) {

@@ -820,23 +820,58 @@ __global__ void guard_gather_kernel(double* __restrict__ out, const CT* __restri
   for (int k = 0; k < d; ++k) out[(long long)j * d + k] = (double)cand[p * ldc + k];
 }
 
-// worst[0] = max over the sample of |var_int8 - var_fp64| / prior_variance  (NaN counts as +inf)
-__global__ void guard_compare_kernel(double* __restrict__ worst, const double* __restrict__ va,
-                                     const double* __restrict__ vb, int n_sample, int m, ObjParams hp) {
+// wnorm[o] += sum of squares of this CTA's share of the packed W_o  (= trace(K_o^-1) once all CTAs have added)
+__global__ void __launch_bounds__(256)
+    guard_wnorm_kernel(double* __restrict__ wnorm, const double* __restrict__ wpack, long long strideWp) {
   __shared__ double red[256];
-  double mx = 0.0;
-  for (int e = threadIdx.x; e < n_sample * m; e += blockDim.x) {
-    const int o = e / n_sample;
-    const double dv = fabs(va[e] - vb[e]) / hp.prior_var[o];
-    mx = (dv != dv) ? __longlong_as_double(0x7ff0000000000000ll) : fmax(mx, dv);
-  }
-  red[threadIdx.x] = mx;
+  const int o = blockIdx.y;
+  const double* W = wpack + (long long)o * strideWp;
+  double s = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < strideWp; e += (long long)gridDim.x * blockDim.x)
+    s = fma(W[e], W[e], s);
+  red[threadIdx.x] = s;
   __syncthreads();
-  for (int s = 128; s; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+  for (int k = 128; k; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
     __syncthreads();
   }
-  if (threadIdx.x == 0) worst[0] = red[0];
+  if (threadIdx.x == 0) atomicAdd(&wnorm[o], red[0]);
+}
+
+// res[0] = max over the sample and the objectives of |var_int8 - var_fp64| / prior_variance (NaN counts as +inf)
+// res[1] = the tolerance it is held to: max(tol, 10 eps cond_upper) with the rigorous upper bound
+//          cond(K + jitter I) <= trace(K + jitter I) * trace((K + jitter I)^-1) = n (var0 + jitter) * |W|_F^2
+// res[2] = 1 if some objective exceeded its tolerance
+__global__ void guard_compare_kernel(double* __restrict__ res, const double* __restrict__ va,
+                                     const double* __restrict__ vb, int n_sample, int m, int n, ObjParams hp,
+                                     double jitter, double tol, const double* __restrict__ wnorm) {
+  __shared__ double red[256];
+  double worst_all = 0.0, tau_all = 0.0, bad = 0.0;
+  for (int o = 0; o < m; ++o) {
+    double mx = 0.0;
+    for (int e = threadIdx.x; e < n_sample; e += blockDim.x) {
+      const double dv = fabs(va[(long long)o * n_sample + e] - vb[(long long)o * n_sample + e]) / hp.prior_var[o];
+      mx = (dv != dv) ? __longlong_as_double(0x7ff0000000000000ll) : fmax(mx, dv);
+    }
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+      __syncthreads();
+    }
+    const double worst = red[0];
+    __syncthreads();
+    const double cond_upper = (double)n * (hp.prior_var[o] + jitter) * wnorm[o];
+    const double tau = fmax(tol, 10.0 * 2.220446049250313e-16 * cond_upper);
+    worst_all = fmax(worst_all, worst);
+    tau_all = fmax(tau_all, tau);
+    if (!(worst <= tau)) bad = 1.0;
+  }
+  if (threadIdx.x == 0) {
+    res[0] = worst_all;
+    res[1] = tau_all;
+    res[2] = bad;
+  }
 }
 
 int guard_samples(long long n_cand, long long stride) {
@@ -853,10 +888,10 @@ size_t oz_guard_workspace_bytes(int n, int m, int d, long long n_cand, long long
          align256(oz_workspace_bytes(make_oz_plan(n, m, S))) + align256(score_workspace_bytes(make_score_plan(n, m, S)));
 }
 
-int oz_guard(double* worst_host, const void* cand, int cand_kind, int ldc, long long n_cand, long long stride,
-             const double* x, int ldx, int n, int d, int m, const unsigned char* wq, const double* wscale,
-             const double* wpack, const double* alpha, const ObjParams& hp, double min_variance, double tol,
-             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+int oz_guard(double* worst_host, double* tau_host, const void* cand, int cand_kind, int ldc, long long n_cand,
+             long long stride, const double* x, int ldx, int n, int d, int m, const unsigned char* wq,
+             const double* wscale, const double* wpack, const double* alpha, const ObjParams& hp, double jitter,
+             double min_variance, double tol, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace_bytes < oz_guard_workspace_bytes(n, m, d, n_cand, stride)) {
     set_error("int8 guard workspace too small");
     return BO_ERR_WORKSPACE;
@@ -867,7 +902,8 @@ int oz_guard(double* worst_host, const void* cand, int cand_kind, int ldc, long 
   double* sample = reinterpret_cast<double*>(ws + off);  off += align256((size_t)S * d * 8);
   double* va = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
   double* vb = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
-  double* worst = reinterpret_cast<double*>(ws + off);   off += 256;
+  double* res = reinterpret_cast<double*>(ws + off);     off += 256;  // [worst, tau, bad, -, wnorm[4]]
+  double* wnorm = res + 4;
   void* ws_i8 = ws + off;
   const size_t ws_i8_bytes = oz_workspace_bytes(make_oz_plan(n, m, S));
   off += align256(ws_i8_bytes);
@@ -890,15 +926,20 @@ int oz_guard(double* worst_host, const void* cand, int cand_kind, int ldc, long 
   rc = score_candidates(ob, sample, BO_CAND_F64, d, S, x, ldx, n, d, m, wpack, alpha, hp, min_variance, ws_f64,
                         ws_f64_bytes, stream);
   if (rc) return rc;
-  guard_compare_kernel<<<1, 256, 0, stream>>>(worst, va, vb, S, m, hp);
+  const long long strideWp = (long long)wpack_tile_offset(round_up(n, TM) / TM) * TILE_DOUBLES;
+  BO_CUDA(cudaMemsetAsync(wnorm, 0, 4 * sizeof(double), stream));
+  guard_wnorm_kernel<<<dim3(device_sm_count(), m), 256, 0, stream>>>(wnorm, wpack, strideWp);
+  BO_LAUNCH_CHECK("guard_wnorm_kernel");
+  guard_compare_kernel<<<1, 256, 0, stream>>>(res, va, vb, S, m, n, hp, jitter, tol, wnorm);
   BO_LAUNCH_CHECK("guard_compare_kernel");
-  double w = 0.0;
-  BO_CUDA(cudaMemcpyAsync(&w, worst, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  double r[3] = {0.0, 0.0, 0.0};
+  BO_CUDA(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, stream));
   BO_CUDA(cudaStreamSynchronize(stream));
-  if (worst_host) *worst_host = w;
-  if (!(w <= tol)) {
+  if (worst_host) *worst_host = r[0];
+  if (tau_host) *tau_host = r[1];
+  if (r[2] != 0.0) {
     set_error("int8 variance engine guard: |var_int8 - var_fp64| / prior_variance = %.3e exceeds %.3e on a sample of "
-              "%d candidates (no fallback: use variance_engine=\"dmma\")", w, tol, S);
+              "%d candidates (no fallback: use variance_engine=\"dmma\")", r[0], r[1], S);
     return BO_ERR_GUARD;
   }
   return BO_OK;

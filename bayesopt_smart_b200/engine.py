@@ -154,6 +154,7 @@ class DeviceGP:
         self.int8_guard_tol = float(int8_guard_tol)
         self.int8_guard_stride = max(1, int(int8_guard_stride))
         self.last_guard_worst: Optional[float] = None  # largest sampled |d var| / prior_variance of the last score()
+        self.last_guard_tolerance: Optional[float] = None  # what it was held to: max(tol, 10 eps cond_upper)
         self.wq: Optional[torch.Tensor] = None
         self.wscale: Optional[torch.Tensor] = None
         self.lib = _lib.load()
@@ -332,12 +333,13 @@ class DeviceGP:
         if int8 and self.int8_guard_tol > 0.0 and n_cand > 0:
             gbytes = self.lib.bo_i8_guard_workspace_bytes(self.n, m, self.d, n_cand, self.int8_guard_stride)
             gws = self.ws.get("i8_guard", gbytes, self.device)
-            worst = ctypes.c_double(0.0)
-            rc = self.lib.bo_i8_guard_f64(ctypes.byref(worst), _ptr(cand), kind, cand.stride(0), n_cand,
-                                          self.int8_guard_stride, _ptr(self.x), self.x.stride(0), self.n, self.d, m,
-                                          _ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack), _ptr(self.alpha), pm, pv,
-                                          pl, float(min_variance), self.int8_guard_tol, _ptr(gws), gbytes, _stream())
-            self.last_guard_worst = worst.value
+            worst, tau = ctypes.c_double(0.0), ctypes.c_double(0.0)
+            rc = self.lib.bo_i8_guard_f64(ctypes.byref(worst), ctypes.byref(tau), _ptr(cand), kind, cand.stride(0),
+                                          n_cand, self.int8_guard_stride, _ptr(self.x), self.x.stride(0), self.n,
+                                          self.d, m, _ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack),
+                                          _ptr(self.alpha), pm, pv, pl, float(self._fit_key[3]), float(min_variance),
+                                          self.int8_guard_tol, _ptr(gws), gbytes, _stream())
+            self.last_guard_worst, self.last_guard_tolerance = worst.value, tau.value
             _lib.check(rc)  # Int8GuardError: the caller decides (there is no silent switch to the FP64 engine)
         return {k: v for k, v in res.items() if v is not None}
 

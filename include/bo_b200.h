@@ -153,20 +153,23 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
  * target -- while the measured error is ~1e-11 because balanced digits make those terms zero-mean.  The guard turns
  * that statistical statement into a checked one: one candidate per window of `stride` candidates (hashed offset
  * inside the window) is scored with BOTH engines from the same factor, and the call returns BO_ERR_GUARD -- no
- * silent fallback -- if max |var_int8 - var_fp64| / prior_variance exceeds `tol`.  The sampled candidates' INT8
+ * silent fallback -- if max |var_int8 - var_fp64| / prior_variance exceeds tau = max(tol, 10 eps cond_upper), the
+ * parity tolerance of SURVEY 8(c) with the rigorous upper bound cond(K + jitter I) <= trace(K + jitter I) *
+ * trace((K + jitter I)^-1) = n (var0 + jitter) |W|_F^2 evaluated on the device (for well-conditioned fits tau is
+ * `tol`, i.e. 1e-9; it widens only where the FP64 result itself is no better).  The sampled candidates' INT8
  * results are bit for bit those of the main pass (a candidate's numbers do not depend on chunking).  If a fraction
  * p of all candidates violated `tol`, a sample of S = ceil(n_cand / stride) misses them with probability
  * (1 - p)^S (stride 4096, 10^6 candidates: S = 245, p = 2 %  ->  0.7 %); errors of this engine come from the
  * quantisation of W and K*, which every candidate shares, so a real failure shows up in essentially every sample.
- * wpack_dev is the FP64 factor of the same fit.  *worst_host receives the largest sampled difference.
- * Synchronising.                                                                                          */
+ * wpack_dev is the FP64 factor of the same fit (jitter: the one it was built with).  *worst_host receives the
+ * largest sampled difference, *tau_host the tolerance it was held to.  Synchronising.                      */
 size_t bo_i8_guard_workspace_bytes(int n, int m, int d, long long n_cand, long long stride);
-int bo_i8_guard_f64(double* worst_host, const void* cand_dev, int cand_kind, int ldc, long long n_cand,
-                    long long stride, const double* x_dev, int ldx, int n, int d, int m, const uint8_t* wq_dev,
-                    const double* wscale_dev, const double* wpack_dev, const double* alpha_dev,
-                    const double* prior_mean_host, const double* prior_variance_host,
-                    const double* length_scales_host, double min_variance, double tol, void* workspace_dev,
-                    size_t workspace_bytes, void* stream);
+int bo_i8_guard_f64(double* worst_host, double* tau_host, const void* cand_dev, int cand_kind, int ldc,
+                    long long n_cand, long long stride, const double* x_dev, int ldx, int n, int d, int m,
+                    const uint8_t* wq_dev, const double* wscale_dev, const double* wpack_dev,
+                    const double* alpha_dev, const double* prior_mean_host, const double* prior_variance_host,
+                    const double* length_scales_host, double jitter, double min_variance, double tol,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
 /* roofline denominator of the INT8 engine: the rate (TOP/s, multiply + add) at which this GPU executes the
  * kernel's own MMA batch (tcgen05.mma.kind::i8 128x64x32, A from TMEM) on resident operands for about `seconds`
  * seconds, one CTA per SM.  Synchronising.                                                              */
