@@ -82,6 +82,9 @@ _SIGNATURES = {
     "bo_pareto_mask_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p]),
     "bo_pareto_mask_against_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_longlong,
                                            c_longlong, c_int, c_void_p]),
+    "bo_pareto_workspace_bytes": (c_size_t, [c_longlong, c_int]),
+    "bo_pareto_mask_filtered_f64": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_void_p, c_size_t,
+                                            c_void_p]),
     "bo_mll_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bo_mll_batched_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _dp, _dp, _dp,
                                    c_int, c_void_p, c_size_t, c_void_p]),

@@ -582,6 +582,15 @@ int bo_pareto_mask_against_f64(uint8_t* mask_dev, const double* y_dev, long long
   return pareto_mask(mask_dev, y_dev, ldy, n, z_dev, ldz, nz, m, (cudaStream_t)stream);
 }
 
+size_t bo_pareto_workspace_bytes(long long n, int m) { return pareto_filtered_workspace_bytes(n, m); }
+
+int bo_pareto_mask_filtered_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m,
+                                void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BO_REQUIRE(mask_dev && y_dev && workspace_dev, "null pointer");
+  BO_REQUIRE(m >= 1 && m <= BO_MAX_OBJECTIVES && ldy >= m, "bad sizes");
+  return pareto_mask_filtered(mask_dev, y_dev, ldy, n, m, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
 size_t bo_mll_workspace_bytes(int n, int m, int n_settings) { return mll_workspace_bytes(n, m, n_settings); }
 
 int bo_mll_batched_f64(double* out_dev, const double* x_dev, int ldx, const double* y_dev, int ldy, int n, int d,

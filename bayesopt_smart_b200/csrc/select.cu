@@ -247,11 +247,17 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------- Pareto
 constexpr int PAR_TILE = 1024;
 
+// n_dev / nz_dev (nullable): the row counts live on the device (stages of the filtered pass below); the grid is
+// then sized for the largest possible n and surplus CTAs leave at once.
 template <int MOBJ>
 __global__ void __launch_bounds__(256)
     pareto_kernel(uint8_t* __restrict__ mask, const double* __restrict__ y, long long ldy, long long n,
-                  const double* __restrict__ z, long long ldz, long long nz) {
+                  const double* __restrict__ z, long long ldz, long long nz, const int* __restrict__ n_dev,
+                  const int* __restrict__ nz_dev) {
   __shared__ double zs[MOBJ][PAR_TILE];
+  if (n_dev) n = *n_dev;
+  if (nz_dev) nz = *nz_dev;
+  if ((long long)blockIdx.x * blockDim.x >= n) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double yi[MOBJ];
 #pragma unroll
@@ -491,17 +497,160 @@ int mask_evaluated(double* out, const double* acq, const void* cand, int cand_ki
   return BO_OK;
 }
 
-int pareto_mask(uint8_t* mask, const double* y, long long ldy, long long n, const double* z, long long ldz,
-                long long nz, int m, cudaStream_t stream) {
+static int pareto_mask_dev(uint8_t* mask, const double* y, long long ldy, long long n, const double* z, long long ldz,
+                           long long nz, int m, const int* n_dev, const int* nz_dev, cudaStream_t stream) {
   if (n <= 0) return BO_OK;
   const unsigned grid = (unsigned)((n + 255) / 256);
   switch (m) {
-    case 1: pareto_kernel<1><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
-    case 2: pareto_kernel<2><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
-    case 3: pareto_kernel<3><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
-    default: pareto_kernel<4><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz); break;
+    case 1: pareto_kernel<1><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz, n_dev, nz_dev); break;
+    case 2: pareto_kernel<2><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz, n_dev, nz_dev); break;
+    case 3: pareto_kernel<3><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz, n_dev, nz_dev); break;
+    default: pareto_kernel<4><<<grid, 256, 0, stream>>>(mask, y, ldy, n, z, ldz, nz, n_dev, nz_dev); break;
   }
   BO_LAUNCH_CHECK("pareto_kernel");
+  return BO_OK;
+}
+
+int pareto_mask(uint8_t* mask, const double* y, long long ldy, long long n, const double* z, long long ldz,
+                long long nz, int m, cudaStream_t stream) {
+  return pareto_mask_dev(mask, y, ldy, n, z, ldz, nz, m, nullptr, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------- filtered Pareto pass
+// Large sets (n > 65 536: the 8 M UCB vectors of BASELINE config 4) are thinned before the n x n test: a point
+// dominated by a member of the exact front of a strided SAMPLE is dominated, and efficient points always survive,
+// so   [sample -> its front, strongest points first -> drop everything it dominates -> compact]  (twice), followed
+// by the plain test among the survivors, gives exactly the mask of the direct test.  Every count stays on the device
+// (no host round trip); grids are sized for the worst case and surplus CTAs exit.
+constexpr int PAR_SAMPLE = 1 << 13;
+
+// sample[j] = cur[j * step], step = ceil(n_cur / PAR_SAMPLE) (so at most PAR_SAMPLE rows); *ns = number of sample rows
+__global__ void pareto_sample_kernel(double* __restrict__ sample, int* __restrict__ ns, const double* __restrict__ cur,
+                                     long long ld, long long n_cur, const int* __restrict__ n_cur_dev, int m) {
+  if (n_cur_dev) n_cur = *n_cur_dev;
+  const long long step = n_cur > PAR_SAMPLE ? (n_cur + PAR_SAMPLE - 1) / PAR_SAMPLE : 1;
+  const long long cnt = (n_cur + step - 1) / step;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) *ns = (int)cnt;
+  if (j >= cnt) return;
+  for (int o = 0; o < m; ++o) sample[j * m + o] = cur[j * step * ld + o];
+}
+
+// front = kept sample rows ordered by the sum of their objectives, descending (NaN sums last): most rows are then
+// dominated within the first few comparisons and their warps leave the loop early.  Ordering only.  *nf = kept rows.
+__global__ void __launch_bounds__(256)
+    pareto_order_front_kernel(double* __restrict__ front, int* __restrict__ nf, const double* __restrict__ sample,
+                              const uint8_t* __restrict__ smask, const int* __restrict__ ns_dev, int m) {
+  const int ns = *ns_dev;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  auto key = [&](int r) {
+    double s = 0.0;
+    for (int o = 0; o < m; ++o) s += sample[(long long)r * m + o];
+    return (s != s) ? -__longlong_as_double(0x7ff0000000000000ll) : s;
+  };
+  const double mine = key(i);
+  int rank = 0, kept = 0;
+  for (int j = 0; j < ns; ++j) {
+    if (!smask[j]) continue;
+    ++kept;
+    const double kj = key(j);
+    if (kj > mine || (kj == mine && j < i)) ++rank;
+  }
+  if (i == 0) *nf = kept;
+  if (!smask[i]) return;
+  for (int o = 0; o < m; ++o) front[(long long)rank * m + o] = sample[(long long)i * m + o];
+}
+
+// survivors (keep[i] != 0) appended to (rows_out, idx_out) with warp-aggregated atomics; order is irrelevant
+__global__ void __launch_bounds__(256)
+    pareto_compact_kernel(double* __restrict__ rows_out, long long* __restrict__ idx_out, int* __restrict__ count,
+                          const double* __restrict__ cur, long long ld, const long long* __restrict__ idx_in,
+                          const uint8_t* __restrict__ keep, long long n_cur, const int* __restrict__ n_cur_dev, int m) {
+  if (n_cur_dev) n_cur = *n_cur_dev;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool k = i < n_cur && keep[i];
+  const unsigned ballot = __ballot_sync(0xffffffffu, k);
+  if (!ballot) return;
+  int base = 0;
+  if (lane == __ffs(ballot) - 1) base = atomicAdd(count, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+  if (k) {
+    const long long slot = base + __popc(ballot & ((1u << lane) - 1));
+    for (int o = 0; o < m; ++o) rows_out[slot * m + o] = cur[i * ld + o];
+    idx_out[slot] = idx_in ? idx_in[i] : i;
+  }
+}
+
+__global__ void pareto_scatter_kernel(uint8_t* __restrict__ mask, const uint8_t* __restrict__ fin,
+                                      const long long* __restrict__ idx, const int* __restrict__ n_dev) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *n_dev && fin[i]) mask[idx[i]] = 1;
+}
+
+size_t pareto_filtered_workspace_bytes(long long n, int m) {
+  const size_t rows = align256((size_t)n * m * sizeof(double)), idx = align256((size_t)n * sizeof(long long));
+  return 2 * (rows + idx) + 2 * align256((size_t)n) + 2 * align256((size_t)(PAR_SAMPLE + 1) * m * sizeof(double)) +
+         align256(PAR_SAMPLE + 1) + 256;
+}
+
+int pareto_mask_filtered(uint8_t* mask, const double* y, long long ldy, long long n, int m, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0) return BO_OK;
+  if (n > 0x7fffffffLL) {
+    set_error("pareto: more than 2^31 - 1 rows");
+    return BO_ERR_INVALID;
+  }
+  if (workspace_bytes < pareto_filtered_workspace_bytes(n, m)) {
+    set_error("pareto workspace too small");
+    return BO_ERR_WORKSPACE;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  size_t off = 0;
+  const size_t rows_b = align256((size_t)n * m * sizeof(double)), idx_b = align256((size_t)n * sizeof(long long));
+  double* rows[2];
+  long long* idx[2];
+  for (int b = 0; b < 2; ++b) {
+    rows[b] = reinterpret_cast<double*>(ws + off);  off += rows_b;
+    idx[b] = reinterpret_cast<long long*>(ws + off); off += idx_b;
+  }
+  uint8_t* keep = ws + off;    off += align256((size_t)n);
+  uint8_t* fin = ws + off;     off += align256((size_t)n);
+  double* sample = reinterpret_cast<double*>(ws + off);  off += align256((size_t)(PAR_SAMPLE + 1) * m * sizeof(double));
+  double* front = reinterpret_cast<double*>(ws + off);   off += align256((size_t)(PAR_SAMPLE + 1) * m * sizeof(double));
+  uint8_t* smask = ws + off;   off += align256(PAR_SAMPLE + 1);
+  int* counts = reinterpret_cast<int*>(ws + off);  // [0] ns, [1] nf, [2] survivors of round 1, [3] of round 2
+  BO_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), stream));
+  BO_CUDA(cudaMemsetAsync(mask, 0, (size_t)n, stream));
+  const unsigned blocks_n = (unsigned)((n + 255) / 256);
+  const unsigned blocks_s = (PAR_SAMPLE + 1 + 255) / 256;
+  const double* cur = y;
+  long long cur_ld = ldy;
+  const long long* cur_idx = nullptr;
+  const int* cur_n = nullptr;  // device count of the current set (nullptr: n, by value)
+  for (int round = 0; round < 2; ++round) {
+    pareto_sample_kernel<<<blocks_s, 256, 0, stream>>>(sample, counts + 0, cur, cur_ld, n, cur_n, m);
+    BO_LAUNCH_CHECK("pareto_sample_kernel");
+    int rc = pareto_mask_dev(smask, sample, m, PAR_SAMPLE + 1, sample, m, PAR_SAMPLE + 1, m, counts + 0, counts + 0,
+                             stream);
+    if (rc) return rc;
+    pareto_order_front_kernel<<<blocks_s, 256, 0, stream>>>(front, counts + 1, sample, smask, counts + 0, m);
+    BO_LAUNCH_CHECK("pareto_order_front_kernel");
+    rc = pareto_mask_dev(keep, cur, cur_ld, n, front, m, PAR_SAMPLE + 1, m, cur_n, counts + 1, stream);
+    if (rc) return rc;
+    pareto_compact_kernel<<<blocks_n, 256, 0, stream>>>(rows[round], idx[round], counts + 2 + round, cur, cur_ld,
+                                                        cur_idx, keep, n, cur_n, m);
+    BO_LAUNCH_CHECK("pareto_compact_kernel");
+    cur = rows[round];
+    cur_ld = m;
+    cur_idx = idx[round];
+    cur_n = counts + 2 + round;
+  }
+  int rc = pareto_mask_dev(fin, cur, m, n, cur, m, n, m, cur_n, cur_n, stream);
+  if (rc) return rc;
+  pareto_scatter_kernel<<<blocks_n, 256, 0, stream>>>(mask, fin, cur_idx, cur_n);
+  BO_LAUNCH_CHECK("pareto_scatter_kernel");
   return BO_OK;
 }
 

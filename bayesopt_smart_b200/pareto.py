@@ -11,7 +11,6 @@ from .engine import _ptr, _stream, require_cuda, to_device
 
 _F64 = torch.float64
 _DIRECT_LIMIT = 1 << 16  # below this the plain n x n kernel is used
-_SAMPLE = 1 << 13
 
 
 def _mask_direct(y: torch.Tensor) -> torch.Tensor:
@@ -33,37 +32,28 @@ def _mask_against(y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     return mask
 
 
+_ws = {}
+
+
 def pareto_mask_device(y: torch.Tensor) -> torch.Tensor:
     """Non-dominated mask (uint8) of an (n, m) CUDA tensor, maximisation, duplicates / NaN rows kept.
 
-    Large sets are first thinned against the exact front of a strided sample (a point dominated by
-    a sample-front member is dominated; efficient points always survive), then the survivors are
-    tested against each other with the plain kernel.  The result equals the direct n x n test.
+    Up to 65 536 rows: the plain n x n warp-ballot kernel.  Larger sets (BASELINE config 4 filters 8 M UCB
+    vectors): ``bo_pareto_mask_filtered_f64`` -- sampling, sample-front ordering, thinning, stream compaction
+    and the final test all run inside the library on the device, with no host synchronisation and no PyTorch
+    sort / boolean indexing.  The result equals the direct n x n test.
     """
     y = y.contiguous()
-    n = y.shape[0]
+    n, m = y.shape
     if n <= _DIRECT_LIMIT:
         return _mask_direct(y)
-    alive = torch.arange(n, device=y.device)
-    cur = y
-    for _ in range(4):
-        if cur.shape[0] <= _DIRECT_LIMIT:
-            break
-        step = max(1, cur.shape[0] // _SAMPLE)
-        sample = cur[::step].contiguous()
-        front = sample[_mask_direct(sample).bool()]
-        # strongest points first: most rows are then dominated within the first few comparisons and
-        # their warps leave the loop early (ordering only; NaN sums go last)
-        order = torch.argsort(torch.nan_to_num(front.sum(dim=1), nan=float("-inf")), descending=True)
-        front = front[order].contiguous()
-        keep = _mask_against(cur, front).bool()
-        if keep.all():
-            break
-        alive = alive[keep]
-        cur = cur[keep].contiguous()
-    final = _mask_direct(cur)
-    mask = torch.zeros(n, dtype=torch.uint8, device=y.device)
-    mask[alive] = final
+    lib = _lib.load()
+    ws_bytes = lib.bo_pareto_workspace_bytes(n, m)
+    ws = _ws.get(y.device)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = _ws[y.device] = torch.empty(int(ws_bytes), dtype=torch.uint8, device=y.device)
+    mask = torch.empty(n, dtype=torch.uint8, device=y.device)
+    _lib.check(lib.bo_pareto_mask_filtered_f64(_ptr(mask), _ptr(y), y.stride(0), n, m, _ptr(ws), ws_bytes, _stream()))
     return mask
 
 

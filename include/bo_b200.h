@@ -228,6 +228,14 @@ int bo_topk_merge_f64(double* out_val_dev, long long* out_idx_dev, const double*
 int bo_pareto_mask_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m, void* stream);
 int bo_pareto_mask_against_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n,
                                const double* z_dev, long long ldz, long long nz, int m, void* stream);
+/* The same mask for LARGE n (BASELINE config 4 filters the 8 M UCB vectors) entirely on the device: two rounds of
+ * [strided sample -> its exact front, strongest points first -> drop every row it dominates -> stream compaction],
+ * then the plain n_s x n_s test among the survivors and a scatter back to the input order.  Exact: a row dominated
+ * by a sample-front member is dominated, efficient rows always survive.  All counts stay on the device (no host
+ * synchronisation, no sort/compaction outside the library); asynchronous on `stream`.                     */
+size_t bo_pareto_workspace_bytes(long long n, int m);
+int bo_pareto_mask_filtered_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m,
+                                void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------- a11: compute_mll
  * Batched log marginal likelihood.  For setting s in [0, S): every objective o uses

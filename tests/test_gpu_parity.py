@@ -442,6 +442,26 @@ def test_pareto_matches_definition(pkg, n, m):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n,m", [(65_537, 2), (300_000, 3), (150_000, 4)])
+def test_filtered_pareto_pass_equals_the_direct_kernel(pkg, n, m):
+    """The in-library large-n pass (sample fronts, thinning, device-side compaction; no host round trips) must give
+    bit for bit the mask of the plain n x n kernel -- duplicates, ties and NaN rows included."""
+    from bayesopt_smart_b200.engine import to_device
+    from bayesopt_smart_b200.pareto import _mask_direct, pareto_mask_device
+
+    rng = np.random.default_rng(n + m)
+    y = rng.normal(size=(n, m))
+    y[::97] = np.round(y[::97], 1)           # ties
+    best = np.argsort(-y.sum(axis=1))[:50]
+    y[best[:10] + 1] = y[best[:10]]          # duplicates of strong points: both rows stay efficient
+    y[123, 0] = np.nan                       # NaN rows neither dominate nor are dominated
+    yd = to_device(y)
+    direct = _mask_direct(yd)
+    filtered = pareto_mask_device(yd)
+    assert torch.equal(direct, filtered)
+    assert 0 < int(direct.sum().item()) < n and bool(direct[123].item())
+
+
 def test_pareto_all_efficient_and_empty(pkg):
     t = np.linspace(0, 1, 4000)
     y = np.stack([t, 1 - t], axis=1)
