@@ -81,7 +81,24 @@ struct TileLoader {
 
 template <int AMODE, int BMODE>
 __global__ void __launch_bounds__(128) gemm64_kernel(GemmArgs g) {
-  if (g.lower_only && blockIdx.x > blockIdx.y) return;
+  // lower_only: the grid is the LIST of tiles on or below the diagonal (no empty CTAs: a 60 x 60-tile trailing update
+  // of 128 matrices would otherwise dispatch 230 000 CTAs that return at once).  Tile rows by < NX hold by + 1 tiles,
+  // the rows below hold NX tiles each.
+  int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  if (g.lower_only) {
+    const int NX = (g.N + GB - 1) / GB;
+    const int t = blockIdx.x, tri = NX * (NX + 1) / 2;
+    if (t < tri) {
+      int by = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // estimate; the two loops make it exact
+      while (by * (by + 1) / 2 > t) --by;
+      while ((by + 1) * (by + 2) / 2 <= t) ++by;
+      tile_y = by;
+      tile_x = t - by * (by + 1) / 2;
+    } else {
+      tile_y = NX + (t - tri) / NX;
+      tile_x = (t - tri) % NX;
+    }
+  }
   __shared__ __align__(16) double As[2][TileLoader<AMODE>::smem_doubles];
   __shared__ __align__(16) double Bs[2][TileLoader<BMODE>::smem_doubles];
 
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(128) gemm64_kernel(GemmArgs g) {
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int g8 = lane >> 2, t4 = lane & 3;
-  const int row0 = blockIdx.y * GB, col0 = blockIdx.x * GB;
+  const int row0 = tile_y * GB, col0 = tile_x * GB;
   const double* A = g.A + (long long)blockIdx.z * g.strideA;
   const double* B = g.B + (long long)blockIdx.z * g.strideB;
   double* C = g.C + (long long)blockIdx.z * g.strideC;
@@ -170,7 +187,13 @@ int gemm(const GemmArgs& a_in, int amode, int bmode, cudaStream_t stream) {
               (((uintptr_t)a.A & 15) == 0) && (((uintptr_t)a.B & 15) == 0) && (a.strideA % 2 == 0) &&
               (a.strideB % 2 == 0);
   a.fast = fast ? 1 : 0;
-  dim3 grid((a.N + GB - 1) / GB, (a.M + GB - 1) / GB, a.batch);
+  const int NX = (a.N + GB - 1) / GB, NY = (a.M + GB - 1) / GB;
+  dim3 grid(NX, NY, a.batch);
+  if (a.lower_only) {  // tiles with tile_x <= tile_y only, as a flat list
+    const long long live = NY >= NX ? (long long)NX * (NX + 1) / 2 + (long long)(NY - NX) * NX
+                                    : (long long)NY * (NY + 1) / 2;
+    grid = dim3((unsigned)live, 1, a.batch);
+  }
   if (amode == 0 && bmode == 0)
     gemm64_kernel<0, 0><<<grid, 128, 0, stream>>>(a);
   else if (amode == 0 && bmode == 1)

@@ -84,51 +84,88 @@ __global__ void __launch_bounds__(256)
 }
 
 // standardise + UCB + exact HVI in one pass over (m, ld) mu / var (numba_kernels.py:538-570, acquisition.py:55-81,
-// then the exact hypervolume improvement instead of acquisition.py:104-108's sum)
-template <int MOBJ>
+// then the exact hypervolume improvement instead of acquisition.py:104-108's sum).  The front tables are staged in
+// shared memory (m = 2: up to HVI2_SMEM_FRONT points, m = 3: up to HVI_SMEM_FRONT), larger fronts are read through L1.
+constexpr int HVI2_SMEM_FRONT = 4096;  // m = 2: 3 x 4096 doubles = 96 KB of dynamic shared memory at most
+
+template <int MOBJ, bool VEC>
 __global__ void __launch_bounds__(256)
     acquisition_hvi_kernel(double* __restrict__ smu_out, double* __restrict__ svar_out, double* __restrict__ ucb_out,
                            double* __restrict__ hvi_out, const double* __restrict__ mu_in,
                            const double* __restrict__ var_in, long long ld, long long n_cand, ObjParams hp,
-                           HviSpec spec) {
-  __shared__ double sf0[MOBJ == 3 ? HVI_SMEM_FRONT : 1], sf1[MOBJ == 3 ? HVI_SMEM_FRONT : 1];
-  __shared__ double szl[MOBJ == 3 ? HVI_SMEM_FRONT + 1 : 1], srk[MOBJ == 3 ? HVI_SMEM_FRONT : 1];
+                           HviSpec spec, int smem_points) {
+  // dynamic shared memory sized by the host for min(allocated front points, limit): small fronts keep occupancy
+  extern __shared__ double hvi_dyn[];
+  const int SM = smem_points;
+  double* sa = hvi_dyn;
+  double* sb = sa + SM;
+  double* sc = sb + SM;            // m = 3: SM + 1 entries
+  double* sd_ = sc + SM + 1;       // m = 3 only
   const int P = *spec.n_front;
   const int cap = spec.cap;
   const double* f0 = spec.prepared;
-  const double* f1 = spec.prepared + cap;
-  const double* zlev = spec.prepared + 3LL * cap;
+  const double* f1 = spec.prepared + cap;              // m = 2: h
+  const double* t2 = spec.prepared + (MOBJ == 3 ? 3LL : 2LL) * cap;  // m = 2: S;  m = 3: zlev
   const double* rank2 = spec.prepared + 4LL * cap + 1;
-  if (MOBJ == 3 && P <= HVI_SMEM_FRONT) {
+  if (P <= SM) {
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
-      sf0[p] = f0[p];
-      sf1[p] = f1[p];
-      srk[p] = rank2[p];
-      szl[p] = zlev[p];
+      sa[p] = f0[p];
+      sb[p] = f1[p];
+      sc[p] = t2[p];
+      if (MOBJ == 3) sd_[p] = rank2[p];
     }
-    if (threadIdx.x == 0) szl[P] = zlev[P];
+    if (MOBJ == 3 && threadIdx.x == 0) sc[P] = t2[P];
     __syncthreads();
-    f0 = sf0; f1 = sf1; zlev = szl; rank2 = srk;
+    f0 = sa; f1 = sb; t2 = sc; rank2 = sd_;
   }
+  const int top = hvi_top_stride(P);
   double sd[MOBJ];
 #pragma unroll
   for (int o = 0; o < MOBJ; ++o) sd[o] = sqrt(hp.prior_var[o]);
+  // a6, a7 for one candidate (numba_kernels.py:563-570, acquisition.py:52)
+  auto ucb_of = [&](int o, double mu, double var, double& smu, double& svar) {
+    smu = (mu - hp.prior_mean[o]) / sd[o];
+    svar = var / hp.prior_var[o];
+    // beta == 0 (raw vectors passed through bo_hvi_f64): no 0 * inf = NaN from an unused variance slot
+    return hp.beta[o] != 0.0 ? smu + hp.beta[o] * sqrt(fabs(svar)) : smu;
+  };
+  auto hvi_of = [&](const double* u) {
+    if (MOBJ == 2) return hvi2_eval(u[0], u[1], f0, f1, t2, P, top, spec.ref[0], spec.ref[1]);
+    return hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, t2, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
+  };
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC) {
+    // two candidates per thread: 16-byte loads / stores, and two independent search chains in flight per thread
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_cand / 2; p += stride) {
+      const long long i = 2 * p;
+      double ua[MOBJ], ub[MOBJ];
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        const double2 mu = *reinterpret_cast<const double2*>(mu_in + o * ld + i);
+        const double2 va = *reinterpret_cast<const double2*>(var_in + o * ld + i);
+        double2 smu, svar;
+        ua[o] = ucb_of(o, mu.x, va.x, smu.x, svar.x);
+        ub[o] = ucb_of(o, mu.y, va.y, smu.y, svar.y);
+        if (smu_out) *reinterpret_cast<double2*>(smu_out + o * ld + i) = smu;
+        if (svar_out) *reinterpret_cast<double2*>(svar_out + o * ld + i) = svar;
+        if (ucb_out) *reinterpret_cast<double2*>(ucb_out + o * ld + i) = make_double2(ua[o], ub[o]);
+      }
+      const double ha = hvi_of(ua), hb = hvi_of(ub);
+      if (hvi_out) *reinterpret_cast<double2*>(hvi_out + i) = make_double2(ha, hb);
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += stride) {
     double u[MOBJ];
 #pragma unroll
     for (int o = 0; o < MOBJ; ++o) {
-      const double smu = (mu_in[o * ld + i] - hp.prior_mean[o]) / sd[o];
-      const double svar = var_in[o * ld + i] / hp.prior_var[o];
-      // beta == 0 (raw vectors passed through bo_hvi_f64): no 0 * inf = NaN from an unused variance slot
-      u[o] = hp.beta[o] != 0.0 ? smu + hp.beta[o] * sqrt(fabs(svar)) : smu;
+      double smu, svar;
+      u[o] = ucb_of(o, mu_in[o * ld + i], var_in[o * ld + i], smu, svar);
       if (smu_out) smu_out[o * ld + i] = smu;
       if (svar_out) svar_out[o * ld + i] = svar;
       if (ucb_out) ucb_out[o * ld + i] = u[o];
     }
-    double v;
-    if (MOBJ == 2) v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, P, spec.ref[0], spec.ref[1]);
-    else v = hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, zlev, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
+    const double v = hvi_of(u);
     if (hvi_out) hvi_out[i] = v;
   }
 }
@@ -187,10 +224,31 @@ int acquisition_hvi(double* smu, double* svar, double* ucb, double* hvi_out, con
   long long blocks = (n_cand + 255) / 256;
   const long long cap = 32LL * device_sm_count();
   if (blocks > cap) blocks = cap;
-  if (m == 2)
-    acquisition_hvi_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, hvi_out, mu, var, ld, n_cand, hp, spec);
-  else
-    acquisition_hvi_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(smu, svar, ucb, hvi_out, mu, var, ld, n_cand, hp, spec);
+  const int limit = m == 2 ? HVI2_SMEM_FRONT : HVI_SMEM_FRONT;
+  const int pts = spec.cap < limit ? spec.cap : limit;
+  const size_t smem = (size_t)(m == 2 ? 3 * pts + 1 : 4 * pts + 1) * sizeof(double);
+  auto aligned = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; };
+  const bool vec = (ld % 2 == 0) && (n_cand % 2 == 0) && aligned(smu) && aligned(svar) && aligned(ucb) &&
+                   aligned(hvi_out) && aligned(mu) && aligned(var);
+  const long long items = vec ? n_cand / 2 : n_cand;
+  blocks = (items + 255) / 256;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define BO_HVI_LAUNCH(MO, V)                                                                                    \
+  do {                                                                                                          \
+    int rc = ensure_dynamic_smem(acquisition_hvi_kernel<MO, V>, smem);                                          \
+    if (rc) return rc;                                                                                          \
+    acquisition_hvi_kernel<MO, V><<<(unsigned)blocks, 256, smem, stream>>>(smu, svar, ucb, hvi_out, mu, var, ld, \
+                                                                           n_cand, hp, spec, pts);              \
+  } while (0)
+  if (m == 2) {
+    if (vec) BO_HVI_LAUNCH(2, true);
+    else BO_HVI_LAUNCH(2, false);
+  } else {
+    if (vec) BO_HVI_LAUNCH(3, true);
+    else BO_HVI_LAUNCH(3, false);
+  }
+#undef BO_HVI_LAUNCH
   BO_LAUNCH_CHECK("acquisition_hvi_kernel");
   return BO_OK;
 }

@@ -11,7 +11,8 @@
 // *n_front = live points P.
 //   m = 2:  f0[cap] | h[cap] | S[cap]      h = objective 1 (ascending along the staircase),
 //                                          S[i] = sum_{k<=i} (f0[k] - r0) (h[k] - h[k-1]),  h[-1] = r1
-//           HVI(u) needs two binary searches and O(1) arithmetic -- no cap on P, no shared memory:
+//           HVI(u) needs two binary searches and O(1) arithmetic -- no cap on P (tables in shared memory up to
+//           4096 points, read through L1 beyond that):
 //             a = #{f0 >= u0},  b = first index with h >= u1;  a > b  =>  u is dominated  =>  0
 //             covered = (u0-r0)(h[a-1]-r1) + (S[b-1]-S[a-1]) + (f0[b]-r0)(u1-h[b-1])
 //   m = 3:  f0[cap] | f1[cap] | f2[cap] | zlev[cap+1] | rank2[cap]   (rank2 stored as doubles)
@@ -32,30 +33,28 @@ struct HviSpec {
 };
 
 #ifdef __CUDACC__
+// largest power of two <= P (0 for an empty front): first stride of the branch-free searches below
+__device__ __forceinline__ int hvi_top_stride(int P) { return P > 0 ? 1 << (31 - __clz(P)) : 0; }
+
+// f0 / h / S may point to shared or global memory.  The two searches are branch-free binary searches with a fixed
+// trip count (log2 P + 1 probes each: index arithmetic, one load, one compare, one select per probe).
 __device__ __forceinline__ double hvi2_eval(double u0, double u1, const double* __restrict__ f0,
                                             const double* __restrict__ h, const double* __restrict__ S, int P,
-                                            double r0, double r1) {
+                                            int top, double r0, double r1) {
   const double w0 = u0 - r0, w1 = u1 - r1;
   if (!(w0 > 0.0 && w1 > 0.0)) return 0.0;
-  int lo = 0, hi = P;  // a = number of points with f0 >= u0 (f0 is descending)
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(f0 + mid) >= u0) lo = mid + 1;
-    else hi = mid;
+  int a = 0, b = 0;  // a = #{f0 >= u0} (f0 descending);  b = #{h < u1} = first index with h >= u1 (h ascending)
+  for (int step = top; step > 0; step >>= 1) {
+    const int ja = a + step, jb = b + step;
+    const double fa = f0[min(ja, P) - 1], hb = h[min(jb, P) - 1];
+    a = (ja <= P && fa >= u0) ? ja : a;
+    b = (jb <= P && hb < u1) ? jb : b;
   }
-  const int a = lo;
-  lo = 0, hi = P;  // b = first index with h >= u1 (h is ascending)
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(h + mid) < u1) lo = mid + 1;
-    else hi = mid;
-  }
-  const int b = lo;
   if (a > b) return 0.0;  // some point has f0 >= u0 and h >= u1: u adds nothing
-  const double h_a = a > 0 ? __ldg(h + a - 1) : r1;
+  const double h_a = a > 0 ? h[a - 1] : r1;
   double covered = w0 * (h_a - r1);
-  if (b > a) covered += __ldg(S + b - 1) - (a > 0 ? __ldg(S + a - 1) : 0.0);
-  if (b < P) covered += (__ldg(f0 + b) - r0) * (u1 - (b > 0 ? __ldg(h + b - 1) : r1));
+  if (b > a) covered += S[b - 1] - (a > 0 ? S[a - 1] : 0.0);
+  if (b < P) covered += (f0[b] - r0) * (u1 - (b > 0 ? h[b - 1] : r1));
   return w0 * w1 - covered;
 }
 

@@ -50,11 +50,14 @@ __global__ void __launch_bounds__(256) mll_prepare_y_kernel(double* __restrict__
 
 // one CTA per matrix: forward substitution z = L^-1 yt using the inverted 64x64 diagonal blocks,
 // then the three MLL terms.  z lives in shared memory.
-__global__ void __launch_bounds__(256)
+// 32 warps per matrix: the substitution streams the whole lower triangle of L once (64 MB at n = 4096), and with one
+// CTA per matrix its speed is set by how many loads that CTA keeps in flight (8 warps: 4.5 ms per group of matrices).
+constexpr int SOLVE_THREADS = 1024;
+__global__ void __launch_bounds__(SOLVE_THREADS)
     mll_solve_kernel(double* __restrict__ mll_obj, const double* __restrict__ L, long long ldl, long long strideL,
                      const double* __restrict__ D, long long strideD, const int* __restrict__ info,
                      const double* __restrict__ yt, int n, int npad, int m) {
-  extern __shared__ double zsm[];  // npad (z) + 64 (rhs) + 8 (scratch)
+  extern __shared__ double zsm[];  // npad (z) + 64 (rhs) + 32 (scratch: one partial per warp)
   double* z = zsm;
   double* rhs = zsm + npad;
   double* scratch = rhs + 64;
@@ -67,9 +70,10 @@ __global__ void __launch_bounds__(256)
   const int nblk = npad / 64;
   for (int jb = 0; jb < nblk; ++jb) {
     const int r0 = jb * 64;
-    // rhs[r] = yt[r0+r] - sum_{k<r0} L[r0+r][k] z[k]; warp w owns rows 8w..8w+7
-    for (int rr = 0; rr < 8; ++rr) {
-      const int r = warp * 8 + rr;
+    // rhs[r] = yt[r0+r] - sum_{k<r0} L[r0+r][k] z[k]; warp w owns rows 2w, 2w+1
+    constexpr int ROWS_PER_WARP = 64 / (SOLVE_THREADS / 32);
+    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+      const int r = warp * ROWS_PER_WARP + rr;
       const double* Lr = Lb + (long long)(r0 + r) * ldl;
       double s = 0.0;
       for (int k = lane; k < r0; k += 32) s = fma(Lr[k], z[k], s);
@@ -78,8 +82,8 @@ __global__ void __launch_bounds__(256)
       if (lane == 0) rhs[r] = yo[r0 + r] - s;
     }
     __syncthreads();
-    // z[r0 + r] = sum_{c<=r} Dinv[r][c] rhs[c]; 4 threads per row
-    {
+    // z[r0 + r] = sum_{c<=r} Dinv[r][c] rhs[c]; 4 threads per row (the first 256 threads)
+    if (threadIdx.x < 256) {
       const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
       const double* Dr = Db + (long long)jb * 4096 + r * 64;
       double s = 0.0;
@@ -323,7 +327,7 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
   mll_prepare_y_kernel<<<m, 256, 0, stream>>>(yt, y, ldy, n, npad, hp0);
   BO_LAUNCH_CHECK("mll_prepare_y_kernel");
 
-  const size_t solve_smem = (size_t)(npad + 64 + 8) * sizeof(double);
+  const size_t solve_smem = (size_t)(npad + 64 + 32) * sizeof(double);
   {
     const int rc_attr = ensure_dynamic_smem(mll_solve_kernel, solve_smem);
     if (rc_attr) return rc_attr;
@@ -345,7 +349,7 @@ int mll_batched(double* out, const double* x, int ldx, const double* y, int ldy,
     BO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * g * m, stream));
     int rc = cholesky_blocked(A, npad, strideA, npad, g * m, D, strideD, info, pol, jit_dev + s0, 0.0, m, stream);
     if (rc) return rc;
-    mll_solve_kernel<<<g * m, 256, solve_smem, stream>>>(vals + (long long)s0 * m, A, npad, strideA, D, strideD, info,
+    mll_solve_kernel<<<g * m, SOLVE_THREADS, solve_smem, stream>>>(vals + (long long)s0 * m, A, npad, strideA, D, strideD, info,
                                                          yt, n, npad, m);
     BO_LAUNCH_CHECK("mll_solve_kernel");
   }

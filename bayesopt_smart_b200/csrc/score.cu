@@ -134,6 +134,21 @@ constexpr size_t TR_SMEM = (size_t)TR_STAGES * 2 * TILE_DOUBLES * sizeof(double)
                            + 2 * 2 * TN * sizeof(double)                           // epilogue exchange
                            + 2 * TR_STAGES * sizeof(uint64_t);
 
+// unit index -> (objective o, row-block pair pr, candidate tile c).  Candidate tiles are taken in groups of `group`:
+// within a group every pair of every tile is scheduled back to back (pair slower, tile fastest), so the K* tiles of
+// the group (group * npad * 128 * 8 bytes) are fetched from HBM once and re-read by the other pairs from L2.  With
+// group = live_tiles this is the plain (o, pr, c) order, in which a K* tile comes from HBM once per pair.
+__device__ __forceinline__ void trmm_decode(int u, int live_tiles, int npairs, int group, int& o, int& pr, int& c) {
+  const int per_obj = live_tiles * npairs;
+  o = u / per_obj;
+  const int rem = u - o * per_obj;
+  const int cg = rem / (group * npairs);
+  const int r2 = rem - cg * group * npairs;
+  const int in_group = min(group, live_tiles - cg * group);
+  pr = r2 / in_group;
+  c = cg * group + (r2 - pr * in_group);
+}
+
 // Persistent: the grid is one CTA per SM; CTA b walks work units b, b + gridDim.x, ...  A unit is
 // (objective o, row-block pair pr, candidate tile c) with the candidate tile fastest, so the CTAs resident at
 // any time stream the same W tiles (L2 hits).  The producer lane runs ahead across unit boundaries: the tiles
@@ -141,7 +156,7 @@ constexpr size_t TR_SMEM = (size_t)TR_STAGES * 2 * TILE_DOUBLES * sizeof(double)
 __global__ void __launch_bounds__(TR_THREADS, 1)
     trmm_sumsq_kernel(double* __restrict__ part, long long ld_chunk, const double* __restrict__ Wp,
                       long long strideWp, const double* __restrict__ Kp, int nb, int chunk_tiles, int live_tiles,
-                      int total_units) {
+                      int total_units, int group) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sA = reinterpret_cast<double*>(smem_raw);
   double* sB = sA + TR_STAGES * TILE_DOUBLES;
@@ -169,9 +184,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         // grid decode uses the live tile count of this chunk; the K* / part layouts use chunk_tiles
-        const int c = u % live_tiles;
-        const int pr = (u / live_tiles) % npairs;
-        const int o = u / (live_tiles * npairs);
+        int o, pr, c;
+        trmm_decode(u, live_tiles, npairs, group, o, pr, c);
         const int ib_first = nb - 1 - pr;  // heavy block first, its light partner second: nb + 1 k-blocks
         const int n_rb = (pr == ib_first) ? 1 : 2;
         const double* Wo = Wp + (long long)o * strideWp;
@@ -205,9 +219,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1)
   uint32_t phase = 0;
   int epi = 0;  // epilogue counter: alternates the exchange buffer
   for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-    const int c = u % live_tiles;
-    const int pr = (u / live_tiles) % npairs;
-    const int o = u / (live_tiles * npairs);
+    int o, pr, c;
+    trmm_decode(u, live_tiles, npairs, group, o, pr, c);
     const int ib_first = nb - 1 - pr;
     const int n_rb = (pr == ib_first) ? 1 : 2;
     for (int rb = 0; rb < n_rb; ++rb, ++epi) {
@@ -373,7 +386,8 @@ __global__ void __launch_bounds__(256)
   finalize_candidate(mu_out, var_out, smu_out, svar_out, ucb_out, ld_out, gi, li, part, meandot, ld_chunk, nb, MOBJ, hp,
                      min_variance, u);
   double v;
-  if (MOBJ == 2) v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, P, spec.ref[0], spec.ref[1]);
+  if (MOBJ == 2)
+    v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, P, hvi_top_stride(P), spec.ref[0], spec.ref[1]);
   else v = hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, zlev, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
   if (acq_out) acq_out[gi] = v;
 }
@@ -638,8 +652,20 @@ int score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind, i
     const unsigned grid = (unsigned)(units < device_sm_count() ? units : device_sm_count());
     const bool prof = profile_enabled();
     if (prof) profile_begin(stream);
+    // K* reuse in L2: groups of grid / npairs tiles, provided one objective's packed W and the group's K* tiles fit
+    // in ~80 MB of the 126 MB L2 together; otherwise the plain order (BO_TRMM_GROUP=0 forces it)
+    int group = tiles;
+    {
+      static const bool no_group = [] {
+        const char* e = getenv("BO_TRMM_GROUP");
+        return e && e[0] == '0';
+      }();
+      const long long tile_bytes = (long long)p.npad * TN * sizeof(double);
+      const int g = (int)grid / npairs;
+      if (!no_group && g >= 1 && g < tiles && strideWp * 8 + (long long)g * tile_bytes <= (80LL << 20)) group = g;
+    }
     trmm_sumsq_kernel<<<grid, TR_THREADS, TR_SMEM, stream>>>(part, p.ld_chunk, wpack, strideWp, Kp[b], p.nb,
-                                                             p.chunk_tiles, tiles, units);
+                                                             p.chunk_tiles, tiles, units, group);
     // algorithmic work of this launch: m * N^2 flops per live candidate
     if (prof) {
       const long long live = (remaining < p.ld_chunk ? remaining : p.ld_chunk);
