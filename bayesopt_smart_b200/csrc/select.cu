@@ -519,7 +519,7 @@ int pareto_mask(uint8_t* mask, const double* y, long long ldy, long long n, cons
 // ------------------------------------------------------------------------------------------- filtered Pareto pass
 // Large sets (n > 65 536: the 8 M UCB vectors of BASELINE config 4) are thinned before the n x n test: a point
 // dominated by a member of the exact front of a strided SAMPLE is dominated, and efficient points always survive,
-// so   [sample -> its front, strongest points first -> drop everything it dominates -> compact]  (twice), followed
+// so   [sample -> its front, strongest points first -> drop everything it dominates -> compact]  (four times), followed
 // by the plain test among the survivors, gives exactly the mask of the direct test.  Every count stays on the device
 // (no host round trip); grids are sized for the worst case and surplus CTAs exit.
 constexpr int PAR_SAMPLE = 1 << 13;
@@ -620,7 +620,7 @@ int pareto_mask_filtered(uint8_t* mask, const double* y, long long ldy, long lon
   double* sample = reinterpret_cast<double*>(ws + off);  off += align256((size_t)(PAR_SAMPLE + 1) * m * sizeof(double));
   double* front = reinterpret_cast<double*>(ws + off);   off += align256((size_t)(PAR_SAMPLE + 1) * m * sizeof(double));
   uint8_t* smask = ws + off;   off += align256(PAR_SAMPLE + 1);
-  int* counts = reinterpret_cast<int*>(ws + off);  // [0] ns, [1] nf, [2] survivors of round 1, [3] of round 2
+  int* counts = reinterpret_cast<int*>(ws + off);  // [0] ns, [1] nf, [2 + r] survivors of round r
   BO_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), stream));
   BO_CUDA(cudaMemsetAsync(mask, 0, (size_t)n, stream));
   const unsigned blocks_n = (unsigned)((n + 255) / 256);
@@ -629,7 +629,11 @@ int pareto_mask_filtered(uint8_t* mask, const double* y, long long ldy, long lon
   long long cur_ld = ldy;
   const long long* cur_idx = nullptr;
   const int* cur_n = nullptr;  // device count of the current set (nullptr: n, by value)
-  for (int round = 0; round < 2; ++round) {
+  // four rounds: each samples the SURVIVORS of the previous one, whose sample front hugs the true front more closely
+  // (8 M three-objective UCB vectors: ~10 % / 2 % / 0.5 % / 0.2 % survive); the rounds after the first work on few
+  // rows, so they cost little more than their launches, and they keep the final n_s x n_s test small
+  constexpr int PAR_ROUNDS = 4;
+  for (int round = 0; round < PAR_ROUNDS; ++round) {
     pareto_sample_kernel<<<blocks_s, 256, 0, stream>>>(sample, counts + 0, cur, cur_ld, n, cur_n, m);
     BO_LAUNCH_CHECK("pareto_sample_kernel");
     int rc = pareto_mask_dev(smask, sample, m, PAR_SAMPLE + 1, sample, m, PAR_SAMPLE + 1, m, counts + 0, counts + 0,
@@ -639,12 +643,12 @@ int pareto_mask_filtered(uint8_t* mask, const double* y, long long ldy, long lon
     BO_LAUNCH_CHECK("pareto_order_front_kernel");
     rc = pareto_mask_dev(keep, cur, cur_ld, n, front, m, PAR_SAMPLE + 1, m, cur_n, counts + 1, stream);
     if (rc) return rc;
-    pareto_compact_kernel<<<blocks_n, 256, 0, stream>>>(rows[round], idx[round], counts + 2 + round, cur, cur_ld,
+    pareto_compact_kernel<<<blocks_n, 256, 0, stream>>>(rows[round & 1], idx[round & 1], counts + 2 + round, cur, cur_ld,
                                                         cur_idx, keep, n, cur_n, m);
     BO_LAUNCH_CHECK("pareto_compact_kernel");
-    cur = rows[round];
+    cur = rows[round & 1];
     cur_ld = m;
-    cur_idx = idx[round];
+    cur_idx = idx[round & 1];
     cur_n = counts + 2 + round;
   }
   int rc = pareto_mask_dev(fin, cur, m, n, cur, m, n, m, cur_n, cur_n, stream);

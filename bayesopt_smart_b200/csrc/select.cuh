@@ -15,7 +15,7 @@ int mask_evaluated(double* out, const double* acq, const void* cand, int cand_ki
                    const double* x, int ldx, int n, int d, cudaStream_t stream);
 int pareto_mask(uint8_t* mask, const double* y, long long ldy, long long n, const double* z, long long ldz,
                 long long nz, int m, cudaStream_t stream);
-// the same mask for large n without host round trips: two rounds of thinning against the exact front of a strided
+// the same mask for large n without host round trips: four rounds of thinning against the exact front of a strided
 // sample, stream compaction on the device, then the plain test among the survivors (exact; see select.cu)
 size_t pareto_filtered_workspace_bytes(long long n, int m);
 int pareto_mask_filtered(uint8_t* mask, const double* y, long long ldy, long long n, int m, void* workspace,

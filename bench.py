@@ -613,6 +613,16 @@ def run_hbm_passes(dev, peaks, lib):
                            "seconds": t, "achieved": big * 8 / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": big * 8 / t / 1e9 / peaks["hbm_gbs"],
                            "note": "8 B per score; the sample pass reads 1/stride of them again"}
+    # a10 at BASELINE config 4's size: non-dominated filter of 8 M three-objective vectors, all inside the library
+    from bayesopt_smart_b200.pareto import pareto_mask_device
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    yv = torch.randn(8_000_000, 3, dtype=torch.float64, device=dev, generator=g)
+    t = best_of(lambda: pareto_mask_device(yv), reps=3)
+    out["pareto_filter_8M_x_3"] = {"kernel": "pareto_kernel (sample fronts, thinning, compaction, final test)",
+                                   "seconds": t, "points_per_s": 8_000_000 / t,
+                                   "front_points": int(pareto_mask_device(yv).sum().item()),
+                                   "bytes_first_pass": 8_000_000 * 24, "first_pass_floor_s": 8_000_000 * 24 / (peaks["hbm_gbs"] * 1e9)}
     out["peak_source"] = peaks["hbm_source"]
     return out
 

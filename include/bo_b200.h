@@ -228,7 +228,7 @@ int bo_topk_merge_f64(double* out_val_dev, long long* out_idx_dev, const double*
 int bo_pareto_mask_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n, int m, void* stream);
 int bo_pareto_mask_against_f64(uint8_t* mask_dev, const double* y_dev, long long ldy, long long n,
                                const double* z_dev, long long ldz, long long nz, int m, void* stream);
-/* The same mask for LARGE n (BASELINE config 4 filters the 8 M UCB vectors) entirely on the device: two rounds of
+/* The same mask for LARGE n (BASELINE config 4 filters the 8 M UCB vectors) entirely on the device: four rounds of
  * [strided sample -> its exact front, strongest points first -> drop every row it dominates -> stream compaction],
  * then the plain n_s x n_s test among the survivors and a scatter back to the input order.  Exact: a row dominated
  * by a sample-front member is dominated, efficient rows always survive.  All counts stay on the device (no host
