@@ -278,7 +278,8 @@ class DeviceGP:
 
     # ------------------------------------------------------------------ score
     def score(self, candidates, betas, *, want=("mu", "var", "acq"), out: Optional[Dict[str, torch.Tensor]] = None,
-              min_variance: float = MIN_VARIANCE, hvi: Optional["HviFront"] = None) -> Dict[str, torch.Tensor]:
+              min_variance: float = MIN_VARIANCE, hvi: Optional["HviFront"] = None,
+              guard: bool = True) -> Dict[str, torch.Tensor]:
         """Posterior + UCB + acquisition for every candidate row.  Returns CUDA tensors.
 
         ``want`` picks which arrays are written: mu, var, std_mu, std_var, ucb (each (m, M)), acq (M,).
@@ -316,8 +317,23 @@ class DeviceGP:
         else:
             ws_bytes = self.lib.bo_score_workspace_bytes(self.n, m, n_cand)
             ws = self.ws.get("score", ws_bytes, self.device)
+        # (m, M) outputs may be column slices of wider arrays (slice-wise scoring with overlapped copies): the
+        # leading dimension is their common row stride
+        ld_out = n_cand
+        for key in ("mu", "var", "std_mu", "std_var", "ucb"):
+            t = res[key]
+            if t is None:
+                continue
+            if tuple(t.shape) != (m, n_cand) or (n_cand > 1 and t.stride(1) != 1):
+                raise ValueError(f"output {key!r} must be ({m}, {n_cand}) with unit column stride")
+            ld = t.stride(0) if m > 1 else max(t.stride(0), n_cand)
+            if ld_out not in (n_cand, ld) or ld < n_cand:
+                raise ValueError("all (m, M) outputs must share one leading dimension >= M")
+            ld_out = ld
+        if res["acq"] is not None and (res["acq"].numel() != n_cand or (n_cand > 1 and res["acq"].stride(0) != 1)):
+            raise ValueError(f"output 'acq' must be a contiguous vector of {n_cand} values")
         outs = (_ptr(res["mu"]), _ptr(res["var"]), _ptr(res["std_mu"]), _ptr(res["std_var"]), _ptr(res["ucb"]),
-                _ptr(res["acq"]), n_cand, _ptr(cand), kind, cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0),
+                _ptr(res["acq"]), ld_out, _ptr(cand), kind, cand.stride(0), n_cand, _ptr(self.x), self.x.stride(0),
                 self.n, self.d, m)
         if hvi is not None:
             _lib.check(self.lib.bo_score_hvi_f64(1 if int8 else 0, *outs, _ptr(self.wq) if int8 else _ptr(self.wpack),
@@ -330,18 +346,32 @@ class DeviceGP:
         else:
             _lib.check(self.lib.bo_score_f64(*outs, _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl, pb,
                                              float(min_variance), _ptr(ws), ws_bytes, _stream()))
-        if int8 and self.int8_guard_tol > 0.0 and n_cand > 0:
-            gbytes = self.lib.bo_i8_guard_workspace_bytes(self.n, m, self.d, n_cand, self.int8_guard_stride)
-            gws = self.ws.get("i8_guard", gbytes, self.device)
-            worst, tau = ctypes.c_double(0.0), ctypes.c_double(0.0)
-            rc = self.lib.bo_i8_guard_f64(ctypes.byref(worst), ctypes.byref(tau), _ptr(cand), kind, cand.stride(0),
-                                          n_cand, self.int8_guard_stride, _ptr(self.x), self.x.stride(0), self.n,
-                                          self.d, m, _ptr(self.wq), _ptr(self.wscale), _ptr(self.wpack),
-                                          _ptr(self.alpha), pm, pv, pl, float(self._fit_key[3]), float(min_variance),
-                                          self.int8_guard_tol, _ptr(gws), gbytes, _stream())
-            self.last_guard_worst, self.last_guard_tolerance = worst.value, tau.value
-            _lib.check(rc)  # Int8GuardError: the caller decides (there is no silent switch to the FP64 engine)
+        if guard:
+            self.check_int8_guard(cand, min_variance)
         return {k: v for k, v in res.items() if v is not None}
+
+    def check_int8_guard(self, candidates: torch.Tensor, min_variance: float = MIN_VARIANCE) -> None:
+        """INT8 engine only (no-op otherwise): score one candidate per ``int8_guard_stride`` with BOTH engines from
+        the resident factor and raise ``Int8GuardError`` if they differ by more than the guard tolerance.  ``score``
+        calls this itself unless told ``guard=False`` (slice-wise callers check the whole set once)."""
+        n_cand = candidates.shape[0]
+        if self.variance_engine != "int8" or self.int8_guard_tol <= 0.0 or n_cand == 0:
+            return
+        m = self.m
+        _, pm = _lib.host_doubles(self.prior_mean, m)
+        _, pv = _lib.host_doubles(self.prior_variance, m)
+        _, pl = _lib.host_doubles(self.length_scales, m)
+        gbytes = self.lib.bo_i8_guard_workspace_bytes(self.n, m, self.d, n_cand, self.int8_guard_stride)
+        gws = self.ws.get("i8_guard", gbytes, self.device)
+        worst, tau = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        rc = self.lib.bo_i8_guard_f64(ctypes.byref(worst), ctypes.byref(tau), _ptr(candidates),
+                                      candidate_kind(candidates), candidates.stride(0), n_cand, self.int8_guard_stride,
+                                      _ptr(self.x), self.x.stride(0), self.n, self.d, m, _ptr(self.wq),
+                                      _ptr(self.wscale), _ptr(self.wpack), _ptr(self.alpha), pm, pv, pl,
+                                      float(self._fit_key[3]), float(min_variance), self.int8_guard_tol, _ptr(gws),
+                                      gbytes, _stream())
+        self.last_guard_worst, self.last_guard_tolerance = worst.value, tau.value
+        _lib.check(rc)  # Int8GuardError: the caller decides (there is no silent switch to the FP64 engine)
 
     # ------------------------------------------------------------------ select
     def topk(self, acq: torch.Tensor, k: int, index_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -495,7 +525,31 @@ def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean
         cache = {k: torch.empty((n_cand,) if k == "acq" else (gp.m, n_cand), dtype=_F64, device=dev)
                  for k in ("mu", "var", "std_mu", "std_var", "ucb", "acq")}
         gp._iter_out = cache
-    gp.score(cand_dev, betas, out=cache)
+    # The candidates are scored in slices of four K* chunks; as soon as a slice is finalised its rows of the host
+    # arrays (mu, var, acq: the arrays the reference's `state` exposes) leave over PCIe on the copy stream while the
+    # next slice is being scored.  A candidate's numbers do not depend on the slicing (fixed-order reductions).
+    main = torch.cuda.current_stream(dev)
+    side = getattr(gp, "_copy_stream", None)
+    if side is None:
+        side = gp._copy_stream = torch.cuda.Stream(dev)
+    host = {key: mirror.get(key, tuple(cache[key].shape)) for key in want_host}
+    slice_len = 4 * 4 * device_info()["sm_count"] * _lib.BO_TILE if want_host else n_cand
+    for s0 in range(0, n_cand, max(slice_len, 1)):
+        s1 = min(n_cand, s0 + slice_len)
+        part = {key: (v[s0:s1] if v.dim() == 1 else v[:, s0:s1]) for key, v in cache.items()}
+        gp.score(cand_dev[s0:s1], betas, out=part, guard=False)
+        if want_host:
+            done = main.record_event()
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                for key in want_host:  # row by row: contiguous pinned <- contiguous device, truly asynchronous
+                    src = cache[key]
+                    if src.dim() == 1:
+                        host[key][s0:s1].copy_(src[s0:s1], non_blocking=True)
+                    else:
+                        for o in range(src.shape[0]):
+                            host[key][o, s0:s1].copy_(src[o, s0:s1], non_blocking=True)
+    gp.check_int8_guard(cand_dev)  # INT8 engine only: one sampled cross-check for the whole candidate set
     k = min(n_cand, batch_size + 16)
     vals, idx = gp.topk(cache["acq"], k, index_base)
     flags = gp.match_rows(idx, cand_dev, x_dev, index_base)
@@ -508,9 +562,7 @@ def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean
     hi.copy_(idx, non_blocking=True)
     hf.copy_(flags, non_blocking=True)
     for key in want_host:
-        h = mirror.get(key, tuple(cache[key].shape))
-        h.copy_(cache[key], non_blocking=True)
-        res[key] = h.numpy()
+        res[key] = host[key].numpy()
     torch.cuda.synchronize(dev)
     keep = (hf.numpy() == 0) & (hi.numpy() >= 0)
     if keep.sum() < batch_size and k < n_cand:  # rare: the slack was eaten by already-evaluated rows

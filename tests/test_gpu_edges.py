@@ -208,3 +208,31 @@ def test_optimize_with_replaced_input_space_uses_it(pkg):
     bo.optimize()
     new_rows = bo.x_vector[6:10]
     assert np.all(new_rows[:, 0] % 2 == 0)
+
+
+@pytest.mark.parametrize("engine", ["dmma", "int8"])
+def test_host_buffer_iteration_slices_equal_single_shot(pkg, engine):
+    """engine.hot_path_iteration (the end-to-end call bench.py times): host buffers in, the candidate set scored in
+    slices with the device-to-host copies of finished slices overlapping the next slice -- the host arrays must be bit
+    for bit those of one DeviceGP.score over the whole set, and the batch the one DeviceGP.select picks."""
+    from bayesopt_smart_b200.engine import DeviceGP, PinnedMirror, hot_path_iteration, to_device
+
+    n, d, m, n_cand = 200, 6, 2, 700_001  # more than two slices of 4 * 4 * SMs * 128 candidates, ragged tail
+    x, y, mu0, var0 = orc.make_training_set("zdt1", n, d, seed=0)
+    ls, betas = np.full(m, 0.3), np.full(m, 2.0)
+    cand = np.random.default_rng(9).random((n_cand, d))
+    cand[77] = x[3]
+    gp = DeviceGP(variance_engine=engine)
+    res = hot_path_iteration(gp, torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(),
+                             torch.from_numpy(cand).pin_memory(), mu0, var0, ls, betas, n, 3, mirror=PinnedMirror())
+    ref = DeviceGP(variance_engine=engine)
+    ref.fit(x, y, mu0, var0, ls, n)
+    cd = to_device(cand)
+    out = ref.score(cd, betas, want=("mu", "var", "acq"))
+    for key in ("mu", "var", "acq"):
+        assert np.array_equal(res[key], out[key].cpu().numpy()), key
+    _, idx = ref.select(cd, out["acq"], to_device(x), 3)
+    assert np.array_equal(res["idx"], idx) and 77 not in res["idx"].tolist()
+    assert np.array_equal(res["x_next"], cand[idx])
+    if engine == "int8":
+        assert gp.last_guard_worst is not None and gp.last_guard_worst < 1e-10  # one check for the whole set
