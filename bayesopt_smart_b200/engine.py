@@ -525,30 +525,12 @@ def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean
         cache = {k: torch.empty((n_cand,) if k == "acq" else (gp.m, n_cand), dtype=_F64, device=dev)
                  for k in ("mu", "var", "std_mu", "std_var", "ucb", "acq")}
         gp._iter_out = cache
-    # The candidates are scored in slices of four K* chunks; as soon as a slice is finalised its rows of the host
-    # arrays (mu, var, acq: the arrays the reference's `state` exposes) leave over PCIe on the copy stream while the
-    # next slice is being scored.  A candidate's numbers do not depend on the slicing (fixed-order reductions).
-    main = torch.cuda.current_stream(dev)
-    side = getattr(gp, "_copy_stream", None)
-    if side is None:
-        side = gp._copy_stream = torch.cuda.Stream(dev)
+    # One scoring pass over the whole candidate set, then the arrays the reference's `state` exposes go back over
+    # PCIe.  (Scoring in slices so that finished slices leave while the next one is computed was measured and is
+    # slower: 72.1 vs 67.8 ms per cfg2 step with the FP64 engine, 41 vs 24 ms with the INT8 engine -- the persistent
+    # one-CTA-per-SM contraction kernels and the slice-wise copies do not overlap the way the arithmetic suggests.)
+    gp.score(cand_dev, betas, out=cache, guard=False)
     host = {key: mirror.get(key, tuple(cache[key].shape)) for key in want_host}
-    slice_len = 4 * 4 * device_info()["sm_count"] * _lib.BO_TILE if want_host else n_cand
-    for s0 in range(0, n_cand, max(slice_len, 1)):
-        s1 = min(n_cand, s0 + slice_len)
-        part = {key: (v[s0:s1] if v.dim() == 1 else v[:, s0:s1]) for key, v in cache.items()}
-        gp.score(cand_dev[s0:s1], betas, out=part, guard=False)
-        if want_host:
-            done = main.record_event()
-            side.wait_event(done)
-            with torch.cuda.stream(side):
-                for key in want_host:  # row by row: contiguous pinned <- contiguous device, truly asynchronous
-                    src = cache[key]
-                    if src.dim() == 1:
-                        host[key][s0:s1].copy_(src[s0:s1], non_blocking=True)
-                    else:
-                        for o in range(src.shape[0]):
-                            host[key][o, s0:s1].copy_(src[o, s0:s1], non_blocking=True)
     gp.check_int8_guard(cand_dev)  # INT8 engine only: one sampled cross-check for the whole candidate set
     k = min(n_cand, batch_size + 16)
     vals, idx = gp.topk(cache["acq"], k, index_base)
@@ -562,6 +544,7 @@ def hot_path_iteration(gp: DeviceGP, x_vector, y_vector, input_space, prior_mean
     hi.copy_(idx, non_blocking=True)
     hf.copy_(flags, non_blocking=True)
     for key in want_host:
+        host[key].copy_(cache[key], non_blocking=True)
         res[key] = host[key].numpy()
     torch.cuda.synchronize(dev)
     keep = (hf.numpy() == 0) & (hi.numpy() >= 0)

@@ -212,9 +212,9 @@ def test_optimize_with_replaced_input_space_uses_it(pkg):
 
 @pytest.mark.parametrize("engine", ["dmma", "int8"])
 def test_host_buffer_iteration_slices_equal_single_shot(pkg, engine):
-    """engine.hot_path_iteration (the end-to-end call bench.py times): host buffers in, the candidate set scored in
-    slices with the device-to-host copies of finished slices overlapping the next slice -- the host arrays must be bit
-    for bit those of one DeviceGP.score over the whole set, and the batch the one DeviceGP.select picks."""
+    """engine.hot_path_iteration (the end-to-end call bench.py times): pinned host buffers in, host arrays out -- they
+    must be bit for bit those of DeviceGP.score on device-resident inputs, and the batch the one DeviceGP.select
+    picks; scoring the same set in column slices of wider output arrays (strided outputs) changes nothing either."""
     from bayesopt_smart_b200.engine import DeviceGP, PinnedMirror, hot_path_iteration, to_device
 
     n, d, m, n_cand = 200, 6, 2, 700_001  # more than two slices of 4 * 4 * SMs * 128 candidates, ragged tail
@@ -236,3 +236,11 @@ def test_host_buffer_iteration_slices_equal_single_shot(pkg, engine):
     assert np.array_equal(res["x_next"], cand[idx])
     if engine == "int8":
         assert gp.last_guard_worst is not None and gp.last_guard_worst < 1e-10  # one check for the whole set
+    # slice-wise scoring into column slices of the full arrays: a candidate's numbers do not depend on the slicing
+    full = {k: torch.empty_like(v) for k, v in out.items()}
+    for s0 in range(0, n_cand, 250_000):
+        s1 = min(n_cand, s0 + 250_000)
+        ref.score(cd[s0:s1], betas, out={k: (v[s0:s1] if v.dim() == 1 else v[:, s0:s1]) for k, v in full.items()},
+                  guard=False)
+    for key in ("mu", "var", "acq"):
+        assert torch.equal(full[key], out[key]), key
