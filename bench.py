@@ -495,6 +495,8 @@ def run_sharded_job(tag, engine, dev, world, rank, peaks, lib, fit_cache):
                                  "max_abs_var_err_standardised": float(worst[1]), "tolerance": chk["tolerance"],
                                  "within_tolerance": bool(okf.item())},
            "batch_idx": idx.cpu().tolist(), "batch_val": vals.cpu().tolist()}
+    if engine == "int8":
+        blk["guard"] = {"sampled_max_dvar_over_var0": gp.last_guard_worst, "tolerance": gp.last_guard_tolerance}
     if cfg.get("pareto"):
         fr = front.to(torch.int64)
         if world > 1:
@@ -848,7 +850,12 @@ def run_gpu_arm(args):
         for _ in range(2):
             step_e2e(gp8)
         secs8_e2e, _ = timed_steps(lambda: step_e2e(gp8), args.steps)
-        i8 = dict(secs=secs8, secs_e2e=secs8_e2e, prof=pr8, gpu_launches=launches8, dacq=dacq, same_topk=same_topk)
+        i8 = dict(secs=secs8, secs_e2e=secs8_e2e, prof=pr8, gpu_launches=launches8, dacq=dacq, same_topk=same_topk,
+                  guard={"sampled_max_dvar_over_var0": gp8.last_guard_worst, "tolerance": gp8.last_guard_tolerance,
+                         "stride": gp8.int8_guard_stride,
+                         "what": "every INT8 scoring pass (inside the timed steps too) scores one candidate per "
+                                 "stride with the FP64 engine as well and raises if they differ by more than the "
+                                 "tolerance max(1e-9, 10 eps cond_upper)"})
         del gp8, acq_dmma
 
     # ---- the other BASELINE configs as whole jobs (every rank takes part; rank 0 reports)
@@ -957,6 +964,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * i8["secs_e2e"] / args.steps},
             "gpu_launches": i8["gpu_launches"],
             "max_abs_acq_difference_vs_dmma": i8["dacq"], "same_top_batch_as_dmma": i8["same_topk"],
+            "guard": i8["guard"],
             "roofline": roofline_of("int8", i8["prof"], i8["secs"], peak_tflops, peak_i8_tops, peaks["i8_burst_tops"])}),
         "baseline_configs": extras,
         "cpu_baseline": cpu_block,
