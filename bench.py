@@ -373,25 +373,45 @@ def kernel_rooflines(prof: dict, engine: str, step_s: float, peaks: dict) -> dic
     return out
 
 
-def oracle_spot_check(gp, out, cand_dev, x, y, mu0, var0, ls, n, m, count, cond, fit_cache):
-    """CHECKER (not measured, not shipped): `count` evenly spaced candidates of this rank's shard against the CPU
-    oracle's Cholesky-form prediction (oracle/gp_oracle.py chol_fit / chol_predict, pinned to the reference's
-    golden vectors by tests/test_oracle_golden.py).  Tolerance in standardised units: max(1e-9, 10 eps cond)."""
+def oracle_spot_check(out, cand_dev, x, y, mu0, var0, ls, n, m, count, cond, fit_cache, world, rank):
+    """CHECKER (not measured, not shipped): `count` evenly spaced candidates of EVERY rank's shard against the CPU
+    oracle's Cholesky-form prediction (oracle/gp_oracle.py chol_fit / chol_predict, pinned to the reference's golden
+    vectors by tests/test_oracle_golden.py).  The samples (candidate rows + the GPU's mu / var for them) are gathered
+    on rank 0, which factors once per config with all host threads -- eight ranks factoring a 4096 x 4096 system at
+    the same time on 16 cores took minutes.  Tolerance in standardised units: max(1e-9, 10 eps cond)."""
     import torch
-    from oracle import gp_oracle as orc
+    import torch.distributed as dist
+
+    from bayesopt_smart_b200 import distributed as bd
 
     tau = max(1e-9, 10 * EPS * cond)
-    n_c = cand_dev.shape[0]
-    if n_c == 0:
-        return {"candidates": 0, "within_tolerance": True, "tolerance": tau}
-    sel = torch.linspace(0, n_c - 1, min(count, n_c), device=cand_dev.device).long()
-    cs = cand_dev[sel].cpu().numpy()
-    if "fit" not in fit_cache:
-        fit_cache["fit"] = orc.chol_fit(x, y, mu0, var0, ls, n)
-    mu_o, var_o = orc.chol_predict(fit_cache["fit"], x, cs, mu0, var0, ls, n)
-    emu = max(float(np.abs(out["mu"][o][sel].cpu().numpy() - mu_o[o]).max() / np.sqrt(var0[o])) for o in range(m))
-    evar = max(float(np.abs(out["var"][o][sel].cpu().numpy() - var_o[o]).max() / var0[o]) for o in range(m))
-    return {"candidates": int(sel.numel()), "max_abs_mu_err_standardised": emu,
+    dev = cand_dev.device
+    n_c, d = cand_dev.shape
+    pack = torch.full((count, d + 2 * m + 1), float("nan"), dtype=torch.float64, device=dev)  # last column: valid flag
+    if n_c > 0:
+        k = min(count, n_c)
+        sel = torch.linspace(0, n_c - 1, k, device=dev).long()
+        pack[:k, :d] = cand_dev[sel]
+        pack[:k, d:d + m] = out["mu"][:, sel].T
+        pack[:k, d + m:d + 2 * m] = out["var"][:, sel].T
+        pack[:k, -1] = 1.0
+    allp = bd.all_gather_cat(pack) if world > 1 else pack
+    res = torch.zeros(3, dtype=torch.float64, device=dev)  # [max mu err, max var err, checked candidates]
+    if rank == 0:
+        from oracle import gp_oracle as orc
+
+        use_all_host_threads()
+        rows = allp[allp[:, -1] == 1.0].cpu().numpy()
+        if "fit" not in fit_cache:
+            fit_cache["fit"] = orc.chol_fit(x, y, mu0, var0, ls, n)
+        mu_o, var_o = orc.chol_predict(fit_cache["fit"], x, np.ascontiguousarray(rows[:, :d]), mu0, var0, ls, n)
+        emu = max(float(np.abs(rows[:, d + o] - mu_o[o]).max() / np.sqrt(var0[o])) for o in range(m))
+        evar = max(float(np.abs(rows[:, d + m + o] - var_o[o]).max() / var0[o]) for o in range(m))
+        res = torch.tensor([emu, evar, float(rows.shape[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)  # the other ranks hold zeros: this is a broadcast from rank 0
+    emu, evar, checked = (float(v) for v in res.tolist())
+    return {"candidates_per_rank": count, "candidates_checked": int(checked), "max_abs_mu_err_standardised": emu,
             "max_abs_var_err_standardised": evar, "tolerance": tau, "within_tolerance": bool(emu <= tau and evar <= tau)}
 
 
@@ -473,15 +493,9 @@ def run_sharded_job(tag, engine, dev, world, rank, peaks, lib, fit_cache):
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 
-    # ---- assertion 2: oracle spot check of 256 candidates of this rank
-    use_all_host_threads()
-    chk = oracle_spot_check(gp, out, cand, x, y, mu0, var0, ls, n, m, 256, cfg["cond"], fit_cache.setdefault(tag, {}))
-    worst = torch.tensor([chk.get("max_abs_mu_err_standardised", 0.0), chk.get("max_abs_var_err_standardised", 0.0)],
-                         dtype=torch.float64, device=dev)
-    okf = torch.tensor([1 if chk["within_tolerance"] else 0], device=dev)
-    if world > 1:
-        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+    # ---- assertion 2: oracle spot check of 256 candidates of every rank (rank 0 runs the CPU oracle once per config)
+    chk = oracle_spot_check(out, cand, x, y, mu0, var0, ls, n, m, 256, cfg["cond"], fit_cache.setdefault(tag, {}),
+                            world, rank)
     flops = float(total) * m * n * n
     ceiling = peaks["dgemm_tflops"] * 1e12 * world / (m * float(n) * n) if peaks["dgemm_tflops"] else None
     blk = {"variance_engine": engine, "value": total / secs, "unit": UNIT, "ms_per_step": 1e3 * secs,
@@ -491,9 +505,7 @@ def run_sharded_job(tag, engine, dev, world, rank, peaks, lib, fit_cache):
            "frac_of_fp64_ceiling": (total / secs / ceiling) if ceiling else None,
            "rooflines_rank0": kernel_rooflines(pr, engine, secs, peaks),
            "sharded_topk_equals_gathered": bool(flag.item()),
-           "oracle_spot_check": {"candidates_per_rank": chk["candidates"], "max_abs_mu_err_standardised": float(worst[0]),
-                                 "max_abs_var_err_standardised": float(worst[1]), "tolerance": chk["tolerance"],
-                                 "within_tolerance": bool(okf.item())},
+           "oracle_spot_check": chk,
            "batch_idx": idx.cpu().tolist(), "batch_val": vals.cpu().tolist()}
     if engine == "int8":
         blk["guard"] = {"sampled_max_dvar_over_var0": gp.last_guard_worst, "tolerance": gp.last_guard_tolerance}
@@ -694,6 +706,7 @@ def run_cfg1_loop():
 
 # --------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
+    t_start = time.perf_counter()
     import torch
     import torch.distributed as dist
 
@@ -868,11 +881,13 @@ def run_gpu_arm(args):
         for label, tag in jobs:
             extras[label] = {"workload": CONFIGS[tag]["name"], "engines": {}}
             for engine in ("dmma", "int8"):
+                t_blk = time.perf_counter()
                 try:
                     extras[label]["engines"][engine] = run_sharded_job(tag, engine, dev, world, rank, peaks, lib,
                                                                        fit_cache)
                 except Exception as exc:  # noqa: BLE001  (reported, never hidden; the headline line still prints)
                     extras[label]["engines"][engine] = {"error": f"{type(exc).__name__}: {exc}"}
+                extras[label]["engines"][engine]["block_wall_s"] = time.perf_counter() - t_blk  # incl. set-up + checks
         try:
             extras["cfg5"] = run_cfg5(dev, world, rank, peaks, lib)
         except Exception as exc:  # noqa: BLE001
@@ -968,6 +983,7 @@ def run_gpu_arm(args):
             "roofline": roofline_of("int8", i8["prof"], i8["secs"], peak_tflops, peak_i8_tops, peaks["i8_burst_tops"])}),
         "baseline_configs": extras,
         "cpu_baseline": cpu_block,
+        "bench_wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
