@@ -136,22 +136,44 @@ __global__ void __launch_bounds__(256)
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (VEC) {
     // two candidates per thread: 16-byte loads / stores, and two independent search chains in flight per thread
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_cand / 2; p += stride) {
-      const long long i = 2 * p;
+    // all loads of an iteration are issued before any arithmetic, and the loads of the NEXT iteration are in flight
+    // while this one's two searches run (the pass is latency-bound otherwise: ncu long-scoreboard stalls)
+    const long long npair = n_cand / 2;
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double2 mu[MOBJ], va[MOBJ], mu_n[MOBJ], va_n[MOBJ];
+    if (p < npair) {
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        mu[o] = *reinterpret_cast<const double2*>(mu_in + o * ld + 2 * p);
+        va[o] = *reinterpret_cast<const double2*>(var_in + o * ld + 2 * p);
+      }
+    }
+    for (; p < npair; p += stride) {
+      const long long i = 2 * p, pn = p + stride;
+      if (pn < npair) {
+#pragma unroll
+        for (int o = 0; o < MOBJ; ++o) {
+          mu_n[o] = *reinterpret_cast<const double2*>(mu_in + o * ld + 2 * pn);
+          va_n[o] = *reinterpret_cast<const double2*>(var_in + o * ld + 2 * pn);
+        }
+      }
       double ua[MOBJ], ub[MOBJ];
 #pragma unroll
       for (int o = 0; o < MOBJ; ++o) {
-        const double2 mu = *reinterpret_cast<const double2*>(mu_in + o * ld + i);
-        const double2 va = *reinterpret_cast<const double2*>(var_in + o * ld + i);
         double2 smu, svar;
-        ua[o] = ucb_of(o, mu.x, va.x, smu.x, svar.x);
-        ub[o] = ucb_of(o, mu.y, va.y, smu.y, svar.y);
+        ua[o] = ucb_of(o, mu[o].x, va[o].x, smu.x, svar.x);
+        ub[o] = ucb_of(o, mu[o].y, va[o].y, smu.y, svar.y);
         if (smu_out) *reinterpret_cast<double2*>(smu_out + o * ld + i) = smu;
         if (svar_out) *reinterpret_cast<double2*>(svar_out + o * ld + i) = svar;
         if (ucb_out) *reinterpret_cast<double2*>(ucb_out + o * ld + i) = make_double2(ua[o], ub[o]);
       }
       const double ha = hvi_of(ua), hb = hvi_of(ub);
       if (hvi_out) *reinterpret_cast<double2*>(hvi_out + i) = make_double2(ha, hb);
+#pragma unroll
+      for (int o = 0; o < MOBJ; ++o) {
+        mu[o] = mu_n[o];
+        va[o] = va_n[o];
+      }
     }
     return;
   }
