@@ -838,13 +838,40 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) atomicAdd(&wnorm[o], red[0]);
 }
 
+// kinf[o] = max_i sum_j |K_o(x_i, x_j) + jitter delta_ij| = |K_o + jitter I|_inf >= lambda_max  (one CTA per row; RBF
+// entries are positive).  For short length scales this is far below the trace n (var0 + jitter).
+__global__ void __launch_bounds__(256)
+    guard_rowsum_kernel(double* __restrict__ kinf, const double* __restrict__ x, int ldx, int n, int d, ObjParams hp,
+                        double jitter) {
+  __shared__ double red[256];
+  const int i = blockIdx.x, o = blockIdx.y;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double sq = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double diff = x[(long long)i * ldx + k] - x[(long long)j * ldx + k];
+      sq = fma(diff, diff, sq);
+    }
+    s += hp.prior_var[o] * exp(sq * hp.neg_half_inv_ls2[o]);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)  // positive doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(&kinf[o]),
+              (unsigned long long)__double_as_longlong(red[0] + jitter));
+}
+
 // res[0] = max over the sample and the objectives of |var_int8 - var_fp64| / prior_variance (NaN counts as +inf)
 // res[1] = the tolerance it is held to: max(tol, 10 eps cond_upper) with the rigorous upper bound
-//          cond(K + jitter I) <= trace(K + jitter I) * trace((K + jitter I)^-1) = n (var0 + jitter) * |W|_F^2
+//          cond(K + jitter I) <= |K + jitter I|_inf * trace((K + jitter I)^-1) = kinf * |W|_F^2
 // res[2] = 1 if some objective exceeded its tolerance
 __global__ void guard_compare_kernel(double* __restrict__ res, const double* __restrict__ va,
-                                     const double* __restrict__ vb, int n_sample, int m, int n, ObjParams hp,
-                                     double jitter, double tol, const double* __restrict__ wnorm) {
+                                     const double* __restrict__ vb, int n_sample, int m, ObjParams hp, double tol,
+                                     const double* __restrict__ wnorm, const double* __restrict__ kinf) {
   __shared__ double red[256];
   double worst_all = 0.0, tau_all = 0.0, bad = 0.0;
   for (int o = 0; o < m; ++o) {
@@ -861,7 +888,7 @@ __global__ void guard_compare_kernel(double* __restrict__ res, const double* __r
     }
     const double worst = red[0];
     __syncthreads();
-    const double cond_upper = (double)n * (hp.prior_var[o] + jitter) * wnorm[o];
+    const double cond_upper = kinf[o] * wnorm[o];
     const double tau = fmax(tol, 10.0 * 2.220446049250313e-16 * cond_upper);
     worst_all = fmax(worst_all, worst);
     tau_all = fmax(tau_all, tau);
@@ -902,8 +929,9 @@ int oz_guard(double* worst_host, double* tau_host, const void* cand, int cand_ki
   double* sample = reinterpret_cast<double*>(ws + off);  off += align256((size_t)S * d * 8);
   double* va = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
   double* vb = reinterpret_cast<double*>(ws + off);      off += align256((size_t)m * S * 8);
-  double* res = reinterpret_cast<double*>(ws + off);     off += 256;  // [worst, tau, bad, -, wnorm[4]]
+  double* res = reinterpret_cast<double*>(ws + off);     off += 256;  // [worst, tau, bad, -, wnorm[4], kinf[4]]
   double* wnorm = res + 4;
+  double* kinf = res + 8;
   void* ws_i8 = ws + off;
   const size_t ws_i8_bytes = oz_workspace_bytes(make_oz_plan(n, m, S));
   off += align256(ws_i8_bytes);
@@ -927,10 +955,12 @@ int oz_guard(double* worst_host, double* tau_host, const void* cand, int cand_ki
                         ws_f64_bytes, stream);
   if (rc) return rc;
   const long long strideWp = (long long)wpack_tile_offset(round_up(n, TM) / TM) * TILE_DOUBLES;
-  BO_CUDA(cudaMemsetAsync(wnorm, 0, 4 * sizeof(double), stream));
+  BO_CUDA(cudaMemsetAsync(wnorm, 0, 8 * sizeof(double), stream));
   guard_wnorm_kernel<<<dim3(device_sm_count(), m), 256, 0, stream>>>(wnorm, wpack, strideWp);
   BO_LAUNCH_CHECK("guard_wnorm_kernel");
-  guard_compare_kernel<<<1, 256, 0, stream>>>(res, va, vb, S, m, n, hp, jitter, tol, wnorm);
+  guard_rowsum_kernel<<<dim3(n, m), 256, 0, stream>>>(kinf, x, ldx, n, d, hp, jitter);
+  BO_LAUNCH_CHECK("guard_rowsum_kernel");
+  guard_compare_kernel<<<1, 256, 0, stream>>>(res, va, vb, S, m, hp, tol, wnorm, kinf);
   BO_LAUNCH_CHECK("guard_compare_kernel");
   double r[3] = {0.0, 0.0, 0.0};
   BO_CUDA(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, stream));

@@ -44,7 +44,7 @@ int oz_score_candidates(const ScoreOutputs& out, const void* cand, int cand_kind
 
 // Sampled guard of the INT8 engine: one candidate per window of `stride` (hashed offset) is scored with BOTH engines
 // from the same factor; BO_ERR_GUARD if max |var_int8 - var_fp64| / prior_variance exceeds
-// max(tol, 10 eps n (var0 + jitter) |W|_F^2)  (the parity tolerance with a rigorous upper bound of cond).  Synchronising.
+// max(tol, 10 eps |K + jitter I|_inf |W|_F^2)  (the parity tolerance with a rigorous upper bound of cond).  Synchronising.
 size_t oz_guard_workspace_bytes(int n, int m, int d, long long n_cand, long long stride);
 int oz_guard(double* worst_host, double* tau_host, const void* cand, int cand_kind, int ldc, long long n_cand,
              long long stride, const double* x, int ldx, int n, int d, int m, const unsigned char* wq,

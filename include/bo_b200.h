@@ -154,8 +154,8 @@ int bo_score_i8(double* mu_dev, double* var_dev, double* std_mu_dev, double* std
  * that statistical statement into a checked one: one candidate per window of `stride` candidates (hashed offset
  * inside the window) is scored with BOTH engines from the same factor, and the call returns BO_ERR_GUARD -- no
  * silent fallback -- if max |var_int8 - var_fp64| / prior_variance exceeds tau = max(tol, 10 eps cond_upper), the
- * parity tolerance of SURVEY 8(c) with the rigorous upper bound cond(K + jitter I) <= trace(K + jitter I) *
- * trace((K + jitter I)^-1) = n (var0 + jitter) |W|_F^2 evaluated on the device (for well-conditioned fits tau is
+ * parity tolerance of SURVEY 8(c) with the rigorous upper bound cond(K + jitter I) <= |K + jitter I|_inf *
+ * trace((K + jitter I)^-1) = (largest row sum of the Gram matrix) * |W|_F^2 evaluated on the device (for well-conditioned fits tau is
  * `tol`, i.e. 1e-9; it widens only where the FP64 result itself is no better).  The sampled candidates' INT8
  * results are bit for bit those of the main pass (a candidate's numbers do not depend on chunking).  If a fraction
  * p of all candidates violated `tol`, a sample of S = ceil(n_cand / stride) misses them with probability
