@@ -63,6 +63,54 @@ __global__ void hvi_prefix2_kernel(double* __restrict__ prepared, const int* __r
   }
 }
 
+// m = 2: the bucket tables of hvi2_eval (hvi.cuh); one thread per bucket edge, full binary search per edge
+__global__ void __launch_bounds__(HVI2_NB + 1)
+    hvi_buckets2_kernel(double* __restrict__ prepared, const int* __restrict__ n_front, int cap) {
+  const int P = *n_front;
+  const double* f0 = prepared;
+  const double* h = prepared + cap;
+  double* tab = prepared + 3LL * cap;
+  const int k = threadIdx.x;  // 0..NB
+  const double f0_min = P > 0 ? f0[P - 1] : 0.0, f0_max = P > 0 ? f0[0] : 0.0;
+  const double h_min = P > 0 ? h[0] : 0.0, h_max = P > 0 ? h[P - 1] : 0.0;
+  const double w0 = (f0_max - f0_min) / HVI2_NB, w1 = (h_max - h_min) / HVI2_NB;
+  const bool ok0 = w0 > 0.0 && w0 < 1e300, ok1 = w1 > 0.0 && w1 < 1e300;
+  // A[k] = #{f0 >= e_k}: degenerate range -> A = [P, 0, 0, ...] (every lookup then searches the whole front)
+  int a = 0;
+  if (k == 0) a = P;
+  else if (k < HVI2_NB && ok0) {
+    const double e = f0_min + k * w0;
+    int lo = 0, hi = P;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (f0[mid - 1] >= e) lo = mid;
+      else hi = mid - 1;
+    }
+    a = lo;
+  }
+  tab[k] = (double)a;
+  int b = P;
+  if (k == 0) b = 0;
+  else if (k < HVI2_NB && ok1) {
+    const double e = h_min + k * w1;
+    int lo = 0, hi = P;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (h[mid - 1] < e) lo = mid;
+      else hi = mid - 1;
+    }
+    b = lo;
+  }
+  tab[HVI2_NB + 1 + k] = (double)b;
+  if (k == 0) {
+    double* sc = tab + 2 * HVI2_NB + 2;
+    sc[0] = f0_min;
+    sc[1] = ok0 ? 1.0 / w0 : 0.0;
+    sc[2] = h_min;
+    sc[3] = ok1 ? 1.0 / w1 : 0.0;
+  }
+}
+
 // m = 3: rank2[p] = position of p in objective-2-descending order (ties by position), zlev[rank] = objective 2
 __global__ void __launch_bounds__(256)
     hvi_levels3_kernel(double* __restrict__ prepared, const int* __restrict__ n_front, int cap, double r2) {
@@ -99,26 +147,27 @@ __global__ void __launch_bounds__(256)
   const int SM = smem_points;
   double* sa = hvi_dyn;
   double* sb = sa + SM;
-  double* sc = sb + SM;            // m = 3: SM + 1 entries
-  double* sd_ = sc + SM + 1;       // m = 3 only
+  double* sc = sb + SM;            // m = 2: S;  m = 3: zlev (SM + 1 entries)
+  double* sd_ = sc + SM + 1;       // m = 2: bucket tables (HVI2_TAB);  m = 3: rank2
   const int P = *spec.n_front;
   const int cap = spec.cap;
   const double* f0 = spec.prepared;
   const double* f1 = spec.prepared + cap;              // m = 2: h
   const double* t2 = spec.prepared + (MOBJ == 3 ? 3LL : 2LL) * cap;  // m = 2: S;  m = 3: zlev
-  const double* rank2 = spec.prepared + 4LL * cap + 1;
+  const double* t3 = MOBJ == 3 ? spec.prepared + 4LL * cap + 1 : spec.prepared + 3LL * cap;  // rank2 / bucket tables
   if (P <= SM) {
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
       sa[p] = f0[p];
       sb[p] = f1[p];
       sc[p] = t2[p];
-      if (MOBJ == 3) sd_[p] = rank2[p];
+      if (MOBJ == 3) sd_[p] = t3[p];
     }
     if (MOBJ == 3 && threadIdx.x == 0) sc[P] = t2[P];
+    if (MOBJ == 2)
+      for (int p = threadIdx.x; p < HVI2_TAB; p += blockDim.x) sd_[p] = t3[p];
     __syncthreads();
-    f0 = sa; f1 = sb; t2 = sc; rank2 = sd_;
+    f0 = sa; f1 = sb; t2 = sc; t3 = sd_;
   }
-  const int top = hvi_top_stride(P);
   double sd[MOBJ];
 #pragma unroll
   for (int o = 0; o < MOBJ; ++o) sd[o] = sqrt(hp.prior_var[o]);
@@ -130,8 +179,8 @@ __global__ void __launch_bounds__(256)
     return hp.beta[o] != 0.0 ? smu + hp.beta[o] * sqrt(fabs(svar)) : smu;
   };
   auto hvi_of = [&](const double* u) {
-    if (MOBJ == 2) return hvi2_eval(u[0], u[1], f0, f1, t2, P, top, spec.ref[0], spec.ref[1]);
-    return hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, t2, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
+    if (MOBJ == 2) return hvi2_eval(u[0], u[1], f0, f1, t2, t3, P, spec.ref[0], spec.ref[1]);
+    return hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, t2, t3, P, spec.ref[0], spec.ref[1], spec.ref[2]);
   };
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (VEC) {
@@ -196,7 +245,7 @@ __global__ void __launch_bounds__(256)
 
 size_t hvi_front_doubles(int n_points, int m) {
   const size_t cap = n_points > 0 ? (size_t)n_points : 1;
-  return (m == 2 ? 3 * cap : 5 * cap + 1) + 2;  // see the layout in hvi.cuh
+  return (m == 2 ? 3 * cap + HVI2_TAB : 5 * cap + 1) + 2;  // see the layout in hvi.cuh
 }
 
 size_t hvi_workspace_bytes(int n_points, int m) {
@@ -215,6 +264,9 @@ int hvi_prepare(double* prepared, int* n_front, const double* points, long long 
     if (m == 3) {  // zlev[0] = r2 closes the single slab of an empty front
       const double r2 = ref[2];
       BO_CUDA(cudaMemcpyAsync(prepared + 3, &r2, sizeof(double), cudaMemcpyHostToDevice, stream));
+    } else {
+      hvi_buckets2_kernel<<<1, HVI2_NB + 1, 0, stream>>>(prepared, n_front, 1);  // all-zero tables (P = 0)
+      BO_LAUNCH_CHECK("hvi_buckets2_kernel");
     }
     return BO_OK;
   }
@@ -232,6 +284,8 @@ int hvi_prepare(double* prepared, int* n_front, const double* points, long long 
   if (m == 2) {
     hvi_prefix2_kernel<<<1, 32, 0, stream>>>(prepared, n_front, cap, ref[0], ref[1]);
     BO_LAUNCH_CHECK("hvi_prefix2_kernel");
+    hvi_buckets2_kernel<<<1, HVI2_NB + 1, 0, stream>>>(prepared, n_front, cap);
+    BO_LAUNCH_CHECK("hvi_buckets2_kernel");
   } else {
     hvi_levels3_kernel<<<blocks, 256, 0, stream>>>(prepared, n_front, cap, ref[2]);
     BO_LAUNCH_CHECK("hvi_levels3_kernel");
@@ -248,7 +302,7 @@ int acquisition_hvi(double* smu, double* svar, double* ucb, double* hvi_out, con
   if (blocks > cap) blocks = cap;
   const int limit = m == 2 ? HVI2_SMEM_FRONT : HVI_SMEM_FRONT;
   const int pts = spec.cap < limit ? spec.cap : limit;
-  const size_t smem = (size_t)(m == 2 ? 3 * pts + 1 : 4 * pts + 1) * sizeof(double);
+  const size_t smem = (size_t)(m == 2 ? 3 * pts + 1 + HVI2_TAB : 4 * pts + 1) * sizeof(double);
   auto aligned = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; };
   const bool vec = (ld % 2 == 0) && (n_cand % 2 == 0) && aligned(smu) && aligned(svar) && aligned(ucb) &&
                    aligned(hvi_out) && aligned(mu) && aligned(var);

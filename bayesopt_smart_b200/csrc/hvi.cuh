@@ -9,10 +9,10 @@
 // Prepared front (hvi_prepare in hvi.cu; all on the device): points clipped to the reference point, dominated
 // points removed, sorted by objective 0 DESCENDING (ties: objective 1 descending), `cap` = allocated points,
 // *n_front = live points P.
-//   m = 2:  f0[cap] | h[cap] | S[cap]      h = objective 1 (ascending along the staircase),
+//   m = 2:  f0[cap] | h[cap] | S[cap] | tab[HVI2_TAB]     h = objective 1 (ascending along the staircase),
 //                                          S[i] = sum_{k<=i} (f0[k] - r0) (h[k] - h[k-1]),  h[-1] = r1
-//           HVI(u) needs two binary searches and O(1) arithmetic -- no cap on P (tables in shared memory up to
-//           4096 points, read through L1 beyond that):
+//           HVI(u) needs two SHORT searches (bucket tables, below) and O(1) arithmetic -- no cap on P (tables in
+//           shared memory up to 4096 points, read through L1 beyond that):
 //             a = #{f0 >= u0},  b = first index with h >= u1;  a > b  =>  u is dominated  =>  0
 //             covered = (u0-r0)(h[a-1]-r1) + (S[b-1]-S[a-1]) + (f0[b]-r0)(u1-h[b-1])
 //   m = 3:  f0[cap] | f1[cap] | f2[cap] | zlev[cap+1] | rank2[cap]   (rank2 stored as doubles)
@@ -33,23 +33,41 @@ struct HviSpec {
 };
 
 #ifdef __CUDACC__
-// largest power of two <= P (0 for an empty front): first stride of the branch-free searches below
-__device__ __forceinline__ int hvi_top_stride(int P) { return P > 0 ? 1 << (31 - __clz(P)) : 0; }
+// m = 2 bucket tables (HVI2_TAB doubles after S): two searches of log2 P probes each dominated the instruction count
+// of the fused pass, so the prepared front carries, for HVI2_NB equal-width buckets over the front's range of each
+// objective, the search result at every bucket edge:
+//   tab[k]              = A[k] = #{f0 >= f0_min + k w0},  k = 0..NB   (A[NB] forced to 0)
+//   tab[NB + 1 + k]     = B[k] = #{h  <  h_min  + k w1},  k = 0..NB   (B[NB] forced to P)
+//   tab[2 NB + 2 .. +5] = f0_min, 1 / w0, h_min, 1 / w1                (1 / w = 0 for a degenerate range)
+// a(u0) = #{f0 >= u0} then lies in [A[k+2], A[k-1]] for the bucket k of u0 (one bucket of slack on each side absorbs
+// the rounding of the bucket index) and is found by a binary search over that short range -- typically 1-2 probes.
+constexpr int HVI2_NB = 256;
+constexpr int HVI2_TAB = 2 * (HVI2_NB + 1) + 4;
 
-// f0 / h / S may point to shared or global memory.  The two searches are branch-free binary searches with a fixed
-// trip count (log2 P + 1 probes each: index arithmetic, one load, one compare, one select per probe).
+// f0 / h / S / tab may point to shared or global memory
 __device__ __forceinline__ double hvi2_eval(double u0, double u1, const double* __restrict__ f0,
-                                            const double* __restrict__ h, const double* __restrict__ S, int P,
-                                            int top, double r0, double r1) {
+                                            const double* __restrict__ h, const double* __restrict__ S,
+                                            const double* __restrict__ tab, int P, double r0, double r1) {
   const double w0 = u0 - r0, w1 = u1 - r1;
   if (!(w0 > 0.0 && w1 > 0.0)) return 0.0;
-  int a = 0, b = 0;  // a = #{f0 >= u0} (f0 descending);  b = #{h < u1} = first index with h >= u1 (h ascending)
-  for (int step = top; step > 0; step >>= 1) {
-    const int ja = a + step, jb = b + step;
-    const double fa = f0[min(ja, P) - 1], hb = h[min(jb, P) - 1];
-    a = (ja <= P && fa >= u0) ? ja : a;
-    b = (jb <= P && hb < u1) ? jb : b;
+  const double* sc = tab + 2 * HVI2_NB + 2;
+  const int ka = max(0, min(HVI2_NB - 1, (int)fmin(fmax((u0 - sc[0]) * sc[1], 0.0), (double)HVI2_NB)));
+  const int kb = max(0, min(HVI2_NB - 1, (int)fmin(fmax((u1 - sc[2]) * sc[3], 0.0), (double)HVI2_NB)));
+  int lo = (int)tab[min(ka + 2, HVI2_NB)], hi = (int)tab[max(ka - 1, 0)];
+  while (lo < hi) {  // a = #{f0 >= u0}: "f0[j-1] >= u0" holds exactly for j <= a (f0 descending)
+    const int mid = (lo + hi + 1) >> 1;
+    if (f0[mid - 1] >= u0) lo = mid;
+    else hi = mid - 1;
   }
+  const int a = lo;
+  lo = (int)tab[HVI2_NB + 1 + max(kb - 1, 0)];
+  hi = (int)tab[HVI2_NB + 1 + min(kb + 2, HVI2_NB)];
+  while (lo < hi) {  // b = #{h < u1} = first index with h >= u1: "h[j-1] < u1" holds exactly for j <= b (h ascending)
+    const int mid = (lo + hi + 1) >> 1;
+    if (h[mid - 1] < u1) lo = mid;
+    else hi = mid - 1;
+  }
+  const int b = lo;
   if (a > b) return 0.0;  // some point has f0 >= u0 and h >= u1: u adds nothing
   const double h_a = a > 0 ? h[a - 1] : r1;
   double covered = w0 * (h_a - r1);
