@@ -155,10 +155,11 @@ def test_cfg5_full_sweep(pkg):
 
 
 @pytest.mark.parametrize("engine", ["dmma", "int8"])
-@pytest.mark.parametrize("case", ["gp_n1024_d6", "gp_n4096_d6"])
+@pytest.mark.parametrize("case", ["gp_n1024_d6", "gp_n4096_d6", "gp_n4096_d10_zdt2", "gp_n2048_d8_dtlz2"])
 def test_reference_fixtures_at_baseline_scale(pkg, golden, case, engine):
     """both variance engines against outputs of the LIVE reference at the cfg2 training size
-    (N = 1024, M = 4096) and the north-star size (N = 4096, M = 1024) -- not against the builder's own oracle.
+    (N = 1024, M = 4096), the north-star size (N = 4096, M = 1024), cfg3's shape (ZDT2, d = 10, N = 4096) and cfg4's
+    (DTLZ2, d = 8, N = 2048, three objectives) -- not against the builder's own oracle.
     Tolerance max(1e-9, 10 eps cond) in standardised units; the selected batch must be the reference's, and that
     claim is only made after asserting that the reference's ranking gaps exceed twice the observed difference."""
     from bayesopt_smart_b200.engine import DeviceGP, to_device
@@ -187,3 +188,41 @@ def test_reference_fixtures_at_baseline_scale(pkg, golden, case, engine):
     assert np.min(-np.diff(ranked)) > 2.0 * np.abs(acq - g["acq"]).max()
     _, idx = gp.select(cd, out["acq"], to_device(x), b)
     assert np.array_equal(cand[idx], g["x_next"])
+
+
+def test_mll_and_pareto_against_reference_outputs_at_baseline_sizes(pkg, golden):
+    """GPU batched MLL against compute_mll of the LIVE reference on cfg2's and cfg5's training sets (N = 1024 / 4096,
+    jitter = CHOLESKY_JITTER), and the dominance kernel against the reference's masks at n = 2048."""
+    from bayesopt_smart_b200 import numba_kernels as nk
+    from bayesopt_smart_b200.workloads import make_training_set
+
+    g = golden("mll_large")
+    for n in (1024, 4096):
+        x, y, mu0, _ = make_training_set("zdt1", n, 6, seed=0)
+        ls = g[f"n{n}_length_scales"]
+        vals = nk.mll_batched(x, y, mu0, np.stack([ls, ls], axis=1), np.full(len(ls), 1e-8), n)
+        np.testing.assert_allclose(vals, g[f"n{n}_mll"], rtol=1e-8)
+    p = golden("pareto_large")
+    assert np.array_equal(pkg.is_pareto_efficient(p["cloud_y"]), p["cloud_mask"])
+    _, yd, _, _ = make_training_set("dtlz2", 2048, 8, seed=0)
+    assert np.array_equal(pkg.is_pareto_efficient(yd), p["dtlz2_mask"])
+
+
+def test_selection_when_more_than_1024_top_rows_were_evaluated(pkg):
+    """the listed top-k is capped at BO_MAX_TOPK = 1024; when every listed row is an evaluated point the
+    selection masks the evaluated candidates exhaustively (bo_mask_evaluated_f64) and still returns the reference's
+    batch (acquisition.py:134-144: first rows of the ranking that are not evaluated)."""
+    from bayesopt_smart_b200.engine import DeviceGP, to_device
+
+    rng = np.random.default_rng(12)
+    n_cand, d = 300_000, 4
+    cand = rng.random((n_cand, d))
+    acq = rng.normal(size=n_cand)
+    order = np.argsort(-acq)
+    evaluated = cand[order[:1500]]           # the 1500 best candidates were all evaluated already
+    gp = DeviceGP()
+    vals, idx = gp.select(to_device(cand), to_device(acq), to_device(evaluated), 5)
+    assert idx.tolist() == order[1500:1505].tolist()
+    assert np.array_equal(vals, acq[order[1500:1505]])
+    _, want_idx = orc.ref_select_next_batch(cand, acq, evaluated, 5)
+    assert idx.tolist() == list(want_idx)

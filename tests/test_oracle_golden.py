@@ -178,11 +178,15 @@ def baseline_scale_inputs(g):
     return n, x, y, cand, mu0, var0, np.full(m, float(g["length_scale"])), np.full(m, float(g["beta"]))
 
 
-@pytest.mark.parametrize("case", ["gp_n1024_d6", "gp_n4096_d6"])
+BASELINE_SCALE_CASES = ["gp_n1024_d6", "gp_n4096_d6", "gp_n4096_d10_zdt2", "gp_n2048_d8_dtlz2"]
+
+
+@pytest.mark.parametrize("case", BASELINE_SCALE_CASES)
 def test_cholesky_form_matches_reference_at_baseline_scale(golden, case):
     """The Cholesky form the GPU computes (chol_*) against the reference's explicit-inverse outputs at the cfg2
-    training size (N = 1024, cond 1.3e4) and the north-star size (N = 4096, cond 3.5e6): tolerance
-    max(1e-9, 10 eps cond) in standardised units, identical selected batch."""
+    training size (N = 1024, cond 1.3e4), the north-star size (N = 4096, cond 3.5e6), cfg3's (ZDT2, d = 10, N = 4096)
+    and cfg4's (DTLZ2, d = 8, N = 2048, three objectives): tolerance max(1e-9, 10 eps cond) in standardised units
+    (SURVEY 8(c)), identical selected batch."""
     g = golden(case)
     n, x, y, cand, mu0, var0, ls, betas = baseline_scale_inputs(g)
     want = orc.chol_hot_path(x, y, cand, mu0, var0, ls, betas, n, int(g["batch_size"]))
@@ -191,3 +195,28 @@ def test_cholesky_form_matches_reference_at_baseline_scale(golden, case):
         assert np.abs(want["mu"][o] - g["mu"][o]).max() / np.sqrt(var0[o]) <= tau
         assert np.abs(want["var"][o] - g["var"][o]).max() / var0[o] <= tau
     assert np.array_equal(cand[want["idx"]], g["x_next"])
+
+
+def test_mll_matches_reference_at_baseline_sizes(golden):
+    """compute_mll of the live reference on cfg2's training set (N = 1024, four length scales) and -- one setting,
+    6 s of CPU -- on cfg5's (N = 4096): the restatement the cfg5 sweep is checked against is itself pinned there."""
+    from bayesopt_smart_b200.workloads import make_training_set
+
+    g = golden("mll_large")
+    for n, take in ((1024, 4), (4096, 1)):
+        x, y, mu0, _ = make_training_set("zdt1", n, 6, seed=0)
+        assert x.sum() == float(g[f"n{n}_x_checksum"])
+        for ls, want in list(zip(g[f"n{n}_length_scales"], g[f"n{n}_mll"]))[:take]:
+            got = orc.ref_compute_mll(x, y, np.zeros((2, n, n)), mu0, np.ones(2), np.full(2, ls), n)
+            assert abs(got - want) <= 1e-9 * abs(want), (n, ls, got, want)
+
+
+def test_pareto_definition_matches_reference_at_n2048(golden):
+    """is_pareto_efficient of the live reference at n = 2048 (ties, duplicates, a NaN row; cfg4's DTLZ2 objectives)."""
+    from bayesopt_smart_b200.workloads import make_training_set
+
+    g = golden("pareto_large")
+    assert np.array_equal(orc.pareto_mask_definition(g["cloud_y"]), g["cloud_mask"])
+    _, yd, _, _ = make_training_set("dtlz2", 2048, 8, seed=0)
+    assert yd.sum() == float(g["dtlz2_checksum"])
+    assert np.array_equal(orc.pareto_mask_definition(yd), g["dtlz2_mask"])
