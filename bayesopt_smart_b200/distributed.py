@@ -38,6 +38,13 @@ def all_gather_cat(t: torch.Tensor, group=None) -> torch.Tensor:
     if world == 1:
         return t
     t = t.contiguous()
+    if t.is_cuda and dist.get_backend(group) == "gloo":
+        # gloo has no CUDA all-gather: stage through the host (used when several ranks share one GPU in tests; the
+        # lists exchanged here are a few hundred bytes)
+        host = t.cpu()
+        parts = [torch.empty_like(host) for _ in range(world)]
+        dist.all_gather(parts, host, group=group)
+        return torch.cat(parts, dim=0).to(t.device)
     out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     try:
         dist.all_gather_into_tensor(out, t, group=group)

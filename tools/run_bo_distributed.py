@@ -26,9 +26,10 @@ def objective(x):
 def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        # BO_DIST_BACKEND=gloo lets several ranks share one GPU (NCCL refuses duplicate devices): the 1-GPU test box
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl")
+        dist.init_process_group(os.environ.get("BO_DIST_BACKEND", "nccl"))
     trace = []
     np.random.seed(7)  # identical LHS initialisation on every rank
     opt = bo.BayesianOptimization(function=objective, bounds=[(0, 60), (0, 50), (0, 45)], n_objectives=3,
