@@ -131,6 +131,42 @@ __global__ void __launch_bounds__(256)
   zlev[r] = mine;
 }
 
+// m = 3: the 2-D staircase (objectives 0, 1) of the s points of largest objective 2, for every s = 1..P, with prefix
+// areas; one thread per slab walks the points in prepared order (objective 0 descending).  Only for P <= PS.
+__global__ void __launch_bounds__(256)
+    hvi_slabs3_kernel(double* __restrict__ prepared, const int* __restrict__ n_front, int cap, double r0, double r1) {
+  const int P = *n_front;
+  const long long ps = cap < HVI3_SLAB_FRONT ? cap : HVI3_SLAB_FRONT;
+  if (P > ps) return;  // the evaluation falls back to the sweep
+  const double* f0 = prepared;
+  const double* f1 = prepared + cap;
+  const double* rank2 = prepared + 4LL * cap + 1;
+  double* slabs = prepared + 5LL * cap + 1;
+  const long long T = ps * (ps + 1) / 2;
+  double* slab_len = slabs;
+  double* slab_f0 = slabs + ps + 1;
+  double* slab_h = slab_f0 + T;
+  double* slab_S = slab_h + T;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;  // slab index; slab 0 has no active point
+  if (s == 0) slab_len[0] = 0.0;
+  if (s < 1 || s > P) return;
+  const long long off = (long long)s * (s - 1) / 2;
+  const double sd = (double)s;
+  double best1 = r1, acc = 0.0;
+  int len = 0;
+  for (int p = 0; p < P; ++p) {
+    if (rank2[p] < sd && f1[p] > best1) {
+      acc += (f0[p] - r0) * (f1[p] - best1);
+      best1 = f1[p];
+      slab_f0[off + len] = f0[p];
+      slab_h[off + len] = f1[p];
+      slab_S[off + len] = acc;
+      ++len;
+    }
+  }
+  slab_len[s] = (double)len;
+}
+
 // standardise + UCB + exact HVI in one pass over (m, ld) mu / var (numba_kernels.py:538-570, acquisition.py:55-81,
 // then the exact hypervolume improvement instead of acquisition.py:104-108's sum).  The front tables are staged in
 // shared memory (m = 2: up to HVI2_SMEM_FRONT points, m = 3: up to HVI_SMEM_FRONT), larger fronts are read through L1.
@@ -180,6 +216,9 @@ __global__ void __launch_bounds__(256)
   };
   auto hvi_of = [&](const double* u) {
     if (MOBJ == 2) return hvi2_eval(u[0], u[1], f0, f1, t2, t3, P, spec.ref[0], spec.ref[1]);
+    if (P <= HVI3_SLAB_FRONT)  // per-slab staircases (global, through L1); zlev from shared memory
+      return hvi3_eval_slabs(u[0], u[1], u[MOBJ - 1], t2, spec.prepared + 5LL * cap + 1, cap, P, spec.ref[0],
+                             spec.ref[1], spec.ref[2]);
     return hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, t2, t3, P, spec.ref[0], spec.ref[1], spec.ref[2]);
   };
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -245,7 +284,7 @@ __global__ void __launch_bounds__(256)
 
 size_t hvi_front_doubles(int n_points, int m) {
   const size_t cap = n_points > 0 ? (size_t)n_points : 1;
-  return (m == 2 ? 3 * cap + HVI2_TAB : 5 * cap + 1) + 2;  // see the layout in hvi.cuh
+  return (m == 2 ? 3 * cap + HVI2_TAB : 5 * cap + 1 + (size_t)hvi3_slab_doubles((int)cap)) + 2;  // layout: hvi.cuh
 }
 
 size_t hvi_workspace_bytes(int n_points, int m) {
@@ -289,6 +328,9 @@ int hvi_prepare(double* prepared, int* n_front, const double* points, long long 
   } else {
     hvi_levels3_kernel<<<blocks, 256, 0, stream>>>(prepared, n_front, cap, ref[2]);
     BO_LAUNCH_CHECK("hvi_levels3_kernel");
+    const int ps = cap < HVI3_SLAB_FRONT ? cap : HVI3_SLAB_FRONT;
+    hvi_slabs3_kernel<<<(ps + 1 + 255) / 256, 256, 0, stream>>>(prepared, n_front, cap, ref[0], ref[1]);
+    BO_LAUNCH_CHECK("hvi_slabs3_kernel");
   }
   return BO_OK;
 }

@@ -15,11 +15,12 @@
 //           shared memory up to 4096 points, read through L1 beyond that):
 //             a = #{f0 >= u0},  b = first index with h >= u1;  a > b  =>  u is dominated  =>  0
 //             covered = (u0-r0)(h[a-1]-r1) + (S[b-1]-S[a-1]) + (f0[b]-r0)(u1-h[b-1])
-//   m = 3:  f0[cap] | f1[cap] | f2[cap] | zlev[cap+1] | rank2[cap]   (rank2 stored as doubles)
+//   m = 3:  f0[cap] | f1[cap] | f2[cap] | zlev[cap+1] | rank2[cap] | slabs[hvi3_slab_doubles(cap)]   (ints as doubles)
 //           zlev[s] = s-th largest objective 2 (zlev[P] = r2); slab s spans (zlev[s], min(zlev[s-1], u2)] and is
 //           covered by the points with rank2 < s; inside a slab the covered area of the box [r, u] is the
-//           f0-descending sweep.  O(P^2) per candidate; fronts up to 1024 points are swept from shared memory,
-//           larger ones from global memory through L1 (no cap on P).
+//           f0-descending sweep: O(P^2) per candidate.  Fronts of up to 1024 points use per-slab staircases prepared
+//           once instead (hvi3_eval_slabs below: two binary searches per slab, O(P log P)); larger fronts fall back
+//           to the sweep, read from global memory through L1 (no cap on P).
 #pragma once
 #include "common.cuh"
 
@@ -98,6 +99,74 @@ __device__ __forceinline__ double hvi3_eval(double u0, double u1, double u2, con
           covered += (a0 - r0) * (a1 - best1);
           best1 = a1;
         }
+      }
+    }
+    total += thick * (box - covered);
+  }
+  return total;
+}
+
+// m = 3, fronts of up to HVI3_SLAB_FRONT points: per-slab staircases prepared once (hvi_slabs3_kernel).  Slab s
+// (1 <= s <= P, z in (zlev[s], zlev[s-1]]) is covered by the s points of largest objective 2; their 2-D staircase in
+// (objective 0, objective 1) -- the candidate-independent part of the sweep above -- is stored with its prefix areas
+// at offset s (s - 1) / 2 of slab_f0 / slab_h / slab_S, slab_len[s] entries.  A candidate then needs two binary
+// searches per slab instead of a sweep over all points: O(P log P) instead of O(P^2).
+constexpr int HVI3_SLAB_FRONT = 1024;
+__host__ __device__ inline long long hvi3_slab_doubles(int cap) {  // slab_len[PS+1] + 3 * PS (PS + 1) / 2
+  const long long ps = cap < HVI3_SLAB_FRONT ? cap : HVI3_SLAB_FRONT;
+  return (ps + 1) + 3 * (ps * (ps + 1) / 2);
+}
+
+__device__ __forceinline__ double hvi3_eval_slabs(double u0, double u1, double u2, const double* __restrict__ zlev,
+                                                  const double* __restrict__ slabs, int cap, int P, double r0,
+                                                  double r1, double r2) {
+  const double w0 = u0 - r0, w1 = u1 - r1;
+  if (!(w0 > 0.0 && w1 > 0.0 && u2 > r2)) return 0.0;
+  const double box = w0 * w1;
+  const long long ps = cap < HVI3_SLAB_FRONT ? cap : HVI3_SLAB_FRONT;
+  const long long T = ps * (ps + 1) / 2;
+  const double* slab_len = slabs;
+  const double* slab_f0 = slabs + ps + 1;
+  const double* slab_h = slab_f0 + T;
+  const double* slab_S = slab_h + T;
+  // first slab that reaches below u2: zlev is descending, slabs above u2 have no thickness
+  int lo = 0, hi = P;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (zlev[mid] >= u2) lo = mid + 1;
+    else hi = mid;
+  }
+  double total = 0.0;
+  for (int s = lo; s <= P; ++s) {
+    const double z_hi = (s == 0) ? u2 : fmin(zlev[s - 1], u2);
+    const double thick = z_hi - zlev[s];
+    if (!(thick > 0.0)) continue;
+    double covered = 0.0;
+    if (s > 0) {
+      const long long off = (long long)s * (s - 1) / 2;
+      const int len = (int)__ldg(slab_len + s);
+      const double* f0 = slab_f0 + off;
+      const double* h = slab_h + off;
+      int a0 = 0, a1 = len;  // a = #{f0 >= u0} (descending)
+      while (a0 < a1) {
+        const int mid = (a0 + a1 + 1) >> 1;
+        if (__ldg(f0 + mid - 1) >= u0) a0 = mid;
+        else a1 = mid - 1;
+      }
+      int b0 = 0, b1 = len;  // b = #{h < u1} (ascending)
+      while (b0 < b1) {
+        const int mid = (b0 + b1 + 1) >> 1;
+        if (__ldg(h + mid - 1) < u1) b0 = mid;
+        else b1 = mid - 1;
+      }
+      const int a = a0, b = b0;
+      if (a > b) {
+        covered = box;  // an active point dominates (u0, u1): the slab adds nothing
+      } else {
+        const double* S = slab_S + off;
+        covered = w0 * ((a > 0 ? __ldg(h + a - 1) : r1) - r1);
+        if (b > a) covered += __ldg(S + b - 1) - (a > 0 ? __ldg(S + a - 1) : 0.0);
+        if (b < len) covered += (__ldg(f0 + b) - r0) * (u1 - (b > 0 ? __ldg(h + b - 1) : r1));
       }
     }
     total += thick * (box - covered);

@@ -388,6 +388,9 @@ __global__ void __launch_bounds__(256)
   double v;
   if (MOBJ == 2)
     v = hvi2_eval(u[0], u[1], f0, f1, spec.prepared + 2LL * cap, spec.prepared + 3LL * cap, P, spec.ref[0], spec.ref[1]);
+  else if (P <= HVI3_SLAB_FRONT)
+    v = hvi3_eval_slabs(u[0], u[1], u[MOBJ - 1], zlev, spec.prepared + 5LL * cap + 1, cap, P, spec.ref[0], spec.ref[1],
+                        spec.ref[2]);
   else v = hvi3_eval(u[0], u[1], u[MOBJ - 1], f0, f1, zlev, rank2, P, spec.ref[0], spec.ref[1], spec.ref[2]);
   if (acq_out) acq_out[gi] = v;
 }
