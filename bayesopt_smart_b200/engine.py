@@ -170,6 +170,11 @@ class DeviceGP:
         self.last_fit = None     # "full" or "append": how the last fit() produced the factor
         self.y: Optional[torch.Tensor] = None
         self._fit_key = None     # (prior_mean, prior_variance, length_scales, jitter) of the resident factor
+        # resident training rows: device buffers with spare capacity + the host copy they were uploaded from
+        self._x_res: Optional[torch.Tensor] = None
+        self._y_res: Optional[torch.Tensor] = None
+        self._x_host: Optional[np.ndarray] = None
+        self._y_host: Optional[np.ndarray] = None
 
     # ------------------------------------------------------------------ fit
     def _stage_training(self, x_vector, y_vector, n: int, compare: bool = True):
@@ -192,10 +197,10 @@ class DeviceGP:
         if xh.ndim != 2 or yh.ndim != 2 or xh.shape[0] < n or yh.shape[0] < n:
             raise ValueError("x_vector (T,d) and y_vector (T,m) must hold at least current_eval rows")
         xh, yh = xh[:n], yh[:n]
-        hx, hy = getattr(self, "_x_host", None), getattr(self, "_y_host", None)
+        hx, hy = self._x_host, self._y_host
         same = bool(0 < n_old <= n and hx is not None and hx.shape[1] == xh.shape[1] and hy.shape[1] == yh.shape[1]
                     and np.array_equal(xh[:n_old], hx[:n_old]) and np.array_equal(yh[:n_old], hy[:n_old]))
-        res_x, res_y = getattr(self, "_x_res", None), getattr(self, "_y_res", None)
+        res_x, res_y = self._x_res, self._y_res
         if same and res_x is not None and res_x.shape[0] >= n:
             if n > n_old:  # only the new rows cross PCIe; the prefix is already resident
                 res_x[n_old:n].copy_(torch.from_numpy(xh[n_old:n]))
