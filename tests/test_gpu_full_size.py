@@ -230,3 +230,19 @@ def test_selection_when_more_than_1024_top_rows_were_evaluated(pkg):
     assert np.array_equal(vals, acq[order[1500:1505]])
     _, want_idx = orc.ref_select_next_batch(cand, acq, evaluated, 5)
     assert idx.tolist() == list(want_idx)
+
+
+def test_exhaustive_exclusion_with_int64_grid_candidates(pkg):
+    """The same fallback on the reference's own candidate type: an int64 Cartesian grid compared with float64
+    evaluated rows by value (acquisition.py:139), more than 1024 evaluated points at the top of the ranking."""
+    from bayesopt_smart_b200.engine import DeviceGP, grid_candidates, to_device
+
+    bounds = [(0, 80), (0, 60), (0, 50)]
+    cand_dev = grid_candidates(bounds)
+    cand = cand_dev.cpu().numpy()
+    assert cand.dtype == np.int64 and cand.shape == (240_000, 3)
+    acq = np.random.default_rng(4).normal(size=cand.shape[0])
+    order = np.argsort(-acq)
+    evaluated = cand[order[:1100]].astype(np.float64)
+    vals, idx = DeviceGP().select(cand_dev, to_device(acq), to_device(evaluated), 4)
+    assert idx.tolist() == order[1100:1104].tolist()
