@@ -31,6 +31,10 @@ namespace {
 // dimension count (coordinates beyond d are zero on both sides, so the inner loop has no predicates).
 // Rows >= n need no masking: the packed W has zero rows/columns there, and alpha is zero.
 constexpr int KS_ROWS = 256;
+__host__ __device__ constexpr int ks_row_stride(int d, int m) {
+  const int even = (d + m + 1) & ~1;
+  return (even % 8 == 0) ? even + 2 : even;
+}
 
 // 4 CTAs/SM (<= 128 registers); 6 CTAs/SM was measured and is not faster: the kernel is bound by its
 // write stream (8*m*npad bytes per candidate), see DESIGN.md.
@@ -41,9 +45,11 @@ __global__ void __launch_bounds__(128, 4)
                       const double* __restrict__ x, int ldx, int n, int npad, int d, const double* __restrict__ alpha,
                       ObjParams hp) {
   __shared__ double exp_tab[64];
-  // row: D coordinates then MOBJ alphas; odd row stride keeps the 4 rows a warp reads (t = 0..3) in
-  // different banks
-  __shared__ double xs[KS_ROWS][(D + MOBJ) | 1];
+  // row: D coordinates then MOBJ alphas, read as 16-byte pairs (D is even).  The row stride is even (16-byte
+  // alignment) but not a multiple of 8 doubles, so the 4 rows a warp reads at a time (t = 0..3) start 4 banks apart
+  // at least and their 16-byte accesses do not collide.
+  constexpr int RS = ks_row_stride(D, MOBJ);
+  __shared__ __align__(16) double xs[KS_ROWS][RS];
   const int tid = threadIdx.x;
   if (tid < 64) exp_tab[tid] = kExp2Tab[tid];
   const int c = blockIdx.x >> 1;
@@ -87,8 +93,18 @@ __global__ void __launch_bounds__(128, 4)
     for (int kt = r0 / TK; kt < kt_end; ++kt) {
 #pragma unroll
       for (int sp = 0; sp < 2; ++sp) {
-        const double* xa = xs[kt * TK - r0 + (sp * 2 + 0) * 4 + t];
-        const double* xb = xs[kt * TK - r0 + (sp * 2 + 1) * 4 + t];
+        // the two training rows of this k-phase, fetched once as 16-byte pairs (coordinates, then alphas)
+        double xa[RS], xb[RS];
+        {
+          const double2* pa = reinterpret_cast<const double2*>(xs[kt * TK - r0 + (sp * 2 + 0) * 4 + t]);
+          const double2* pb = reinterpret_cast<const double2*>(xs[kt * TK - r0 + (sp * 2 + 1) * 4 + t]);
+#pragma unroll
+          for (int k = 0; k < (D + MOBJ + 1) / 2; ++k) {
+            const double2 a2 = pa[k], b2 = pb[k];
+            xa[2 * k] = a2.x; xa[2 * k + 1] = a2.y;
+            xb[2 * k] = b2.x; xb[2 * k + 1] = b2.y;
+          }
+        }
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           double sa = 0.0, sb = 0.0;
